@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- STN glimpses/sec (forward+backward) on the BASELINE config-5 workload, one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a kernels
+    python bench.py --impl reference --steps K --warmup W    # the reference path's CPU restatement
+
+Workload (BASELINE.json configs[4]): per GPU B = 16384 canvases (canvas x canvas, C = 1),
+8 sequential AIR steps with a distinct theta per step; every step does what an AIR step asks of the
+sampler -- a *read* glimpse (canvas -> glimpse, theta_r) and a *write* glimpse (glimpse -> canvas,
+theta_w), each forward + backward(dU + dtheta).  One bench "step" = those 8 AIR steps over the batch
+= 16 * B glimpses.  Batch shards are independent, so N GPUs run N shards (weak scaling, no collective).
+
+`value`: glimpses/s with inputs resident in HBM (CUDA events, max over ranks).
+`e2e`  : the same 16*B glimpses through the host-buffer entry point mog_stn_fwd_bwd_host (pinned host
+         arrays in, host arrays out, copies inside the timed region).
+`roofline`: algorithmic bytes (fwd 4(F+O)+24, bwd 4(O+F+S)+48 per glimpse, F = distinct
+         source pixels addressed) of the dominant kernel / its mean duration, vs MEASURED_PEAKS.json.
+`cpu_baseline`: oracle C restatement (all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "stn_glimpses_per_sec_fwd_bwd"
+UNIT = "glimpses/s"
+AIR_STEPS = 8
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--canvas", type=int, default=50)
+    p.add_argument("--glimpse", type=int, default=28)
+    p.add_argument("--batch", type=int, default=16384, help="canvases per GPU")
+    p.add_argument("--regime", default="prior", choices=["prior", "full"])
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--cpu-sample", type=int, default=1024, help="canvases in the CPU-baseline sample")
+    p.add_argument("--sweep", action="store_true", help="run the whole config-5 sweep, write profiles/sweep_*.json")
+    p.add_argument("--tag", default="", help="suffix for files written under profiles/")
+    return p.parse_args()
+
+
+def workload_name(a):
+    return (f"C5 STN sweep cell: canvas {a.canvas}x{a.canvas} <-> glimpse {a.glimpse}x{a.glimpse}, {AIR_STEPS} AIR steps "
+            f"(read+write, fwd+bwd dU+dtheta), batch {a.batch}/GPU, theta={a.regime}-like")
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs: the oracle's C restatement, all host threads, bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_workload(a, nsample):
+    from mog_asr_b200 import synth
+    rng = np.random.default_rng(10)
+    U = rng.random((nsample, a.canvas, a.canvas, 1), dtype=np.float32)
+    W = rng.random((nsample, a.glimpse, a.glimpse, 1), dtype=np.float32)
+    gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
+    th_r, th_w = [], []
+    for t in range(AIR_STEPS):
+        s, x, y = gen(nsample, seed=100 + t)
+        th_r.append(synth.theta_read(s, x, y))
+        th_w.append(synth.theta_write(s, x, y))
+    g_r = rng.normal(size=(nsample, a.glimpse, a.glimpse, 1)).astype(np.float32)
+    g_w = rng.normal(size=(nsample, a.canvas, a.canvas, 1)).astype(np.float32)
+    return U, W, th_r, th_w, g_r, g_w
+
+
+def cpu_step(a, wl, nthreads=0):
+    from oracle import stn_ref_c as RC
+    U, W, th_r, th_w, g_r, g_w = wl
+    for t in range(AIR_STEPS):
+        RC.forward(U, th_r[t], (a.glimpse, a.glimpse), nthreads=nthreads)
+        RC.backward(U, th_r[t], (a.glimpse, a.glimpse), g_r, nthreads=nthreads)
+        RC.forward(W, th_w[t], (a.canvas, a.canvas), nthreads=nthreads)
+        RC.backward(W, th_w[t], (a.canvas, a.canvas), g_w, nthreads=nthreads)
+
+
+def cpu_measure(a, steps, warmup, nsample):
+    from oracle import stn_ref_c as RC
+    wl = cpu_workload(a, nsample)
+    for _ in range(warmup):
+        cpu_step(a, wl)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(a, wl)
+    dt = time.perf_counter() - t0
+    cores = RC.max_threads()
+    val = nsample * 2 * AIR_STEPS * steps / dt
+    return dict(value=val, unit=UNIT, cores=cores, kind="port",
+                sample=f"{nsample} canvases x {AIR_STEPS} AIR steps x (read+write) fwd+bwd x {steps} steps, "
+                       f"oracle/stn_ref.c with OpenMP over images ({cores} threads; os.cpu_count()={os.cpu_count()}, "
+                       f"affinity={len(os.sched_getaffinity(0))})"), dt / steps * 1e3
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ms = cpu_measure(a, a.steps, a.warmup, a.cpu_sample)
+    line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps,
+                warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=dict(workload=workload_name(a), note="reference is TF-1.12 Python (not installable "
+                "here); its sampler restated in C (oracle/stn_ref.c), timed on the host cores on a bounded sample"),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    INFO = {"sw_power_cap": 0x4, "gpu_idle": 0x1, "applications_clocks_setting": 0x2, "sync_boost": 0x10}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.ok = index, [], False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvml unavailable"])
+        sel = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        bits = 0
+        for s in sel:
+            bits |= s[2]
+        names = [k for k, v in {**self.BAD, **self.INFO}.items() if bits & v and k != "gpu_idle"]
+        return dict(sm_mhz=float(np.median([s[1] for s in sel])) if sel else None, sm_max_mhz=float(mx),
+                    reasons=names, samples=len(sel))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def footprint_counts(torch, M, theta, in_size, out_size):
+    """F[b] = distinct source pixels image b addresses.  For the axis-aligned thetas of this workload the
+    tap set is a cross product, so F = |{x0,x1 over columns}| * |{y0,y1 over rows}|."""
+    Hs, Ws = in_size
+    Ho, Wo = out_size
+    B = theta.shape[0]
+    F = torch.empty(B, dtype=torch.int64, device=theta.device)
+    step = max(1, (1 << 27) // (Ho * Wo))
+    for b0 in range(0, B, step):
+        c = M.stn_corners(theta[b0:b0 + step], in_size, out_size).view(4, -1, Ho, Wo).long()
+        nb = c.shape[1]
+        xs = torch.zeros((nb, Ws), dtype=torch.bool, device=theta.device)
+        xs.scatter_(1, c[0, :, 0, :], True)
+        xs.scatter_(1, c[1, :, 0, :], True)
+        ys = torch.zeros((nb, Hs), dtype=torch.bool, device=theta.device)
+        ys.scatter_(1, c[2, :, :, 0], True)
+        ys.scatter_(1, c[3, :, :, 0], True)
+        F[b0:b0 + nb] = xs.sum(1) * ys.sum(1)
+    return F
+
+
+class GpuWorkload:
+    def __init__(self, a, dev, seed):
+        import torch
+        import mog_asr_b200 as M
+        from mog_asr_b200 import _lib, synth
+        self.torch, self.M, self.L, self.lib = torch, M, _lib.load(), _lib
+        self.a, self.dev = a, dev
+        B, cs, gs = a.batch, a.canvas, a.glimpse
+        g = torch.Generator(device=dev).manual_seed(seed)
+        self.U = torch.rand((B, cs, cs, 1), device=dev, generator=g)                  # canvases (read source)
+        self.W = torch.rand((AIR_STEPS, B, gs, gs, 1), device=dev, generator=g)       # per-step windows (write source)
+        gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
+        thr, thw = [], []
+        for t in range(AIR_STEPS):
+            s, x, y = gen(B, seed=seed * 1000 + 100 + t)
+            thr.append(synth.theta_read(s, x, y))
+            thw.append(synth.theta_write(s, x, y))
+        self.th_r = torch.tensor(np.stack(thr), device=dev)
+        self.th_w = torch.tensor(np.stack(thw), device=dev)
+        self.g_r = torch.randn((AIR_STEPS, B, gs, gs, 1), device=dev, generator=g)
+        self.g_w = torch.randn((AIR_STEPS, B, cs, cs, 1), device=dev, generator=g)
+        self.out_r = torch.empty((B, gs, gs, 1), device=dev)
+        self.out_w = torch.empty((B, cs, cs, 1), device=dev)
+        self.dU_r = torch.empty((B, cs, cs, 1), device=dev)
+        self.dU_w = torch.empty((B, gs, gs, 1), device=dev)
+        self.dth = torch.empty((B, 6), device=dev)
+        self.stream = torch.cuda.current_stream(dev).cuda_stream
+        self.kinds = ("read_fwd", "read_bwd", "write_fwd", "write_bwd")
+
+    def launch(self, kind, t):
+        a, L, ck = self.a, self.L, self.lib.check
+        B, cs, gs, st = a.batch, a.canvas, a.glimpse, self.stream
+        if kind == "read_fwd":
+            ck(L.mog_stn_forward(self.U.data_ptr(), self.th_r[t].data_ptr(), self.out_r.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), kind)
+        elif kind == "read_bwd":
+            ck(L.mog_stn_backward(self.U.data_ptr(), self.th_r[t].data_ptr(), self.g_r[t].data_ptr(), self.dU_r.data_ptr(),
+                                  self.dth.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), kind)
+        elif kind == "write_fwd":
+            ck(L.mog_stn_forward(self.W[t].data_ptr(), self.th_w[t].data_ptr(), self.out_w.data_ptr(), B, gs, gs, 1, cs, cs, 1, st), kind)
+        else:
+            ck(L.mog_stn_backward(self.W[t].data_ptr(), self.th_w[t].data_ptr(), self.g_w[t].data_ptr(), self.dU_w.data_ptr(),
+                                  self.dth.data_ptr(), B, gs, gs, 1, cs, cs, 1, st), kind)
+
+    def step(self, events=None):
+        torch = self.torch
+        for t in range(AIR_STEPS):
+            for kind in self.kinds:
+                if events is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    self.launch(kind, t)
+                    e1.record()
+                    events[kind].append((e0, e1))
+                else:
+                    self.launch(kind, t)
+
+    def algorithmic_bytes(self):
+        """Mean algorithmic bytes per launch for each kernel kind."""
+        torch, a = self.torch, self.a
+        cs, gs = a.canvas, a.glimpse
+        out = {k: 0.0 for k in self.kinds}
+        for t in range(AIR_STEPS):
+            Fr = footprint_counts(torch, self.M, self.th_r[t], (cs, cs), (gs, gs)).double()
+            Fw = footprint_counts(torch, self.M, self.th_w[t], (gs, gs), (cs, cs)).double()
+            O_r, S_r, O_w, S_w = gs * gs, cs * cs, cs * cs, gs * gs
+            out["read_fwd"] += float((4 * (Fr + O_r) + 24).sum()) / AIR_STEPS
+            out["read_bwd"] += float((4 * (O_r + Fr + S_r) + 48).sum()) / AIR_STEPS
+            out["write_fwd"] += float((4 * (Fw + O_w) + 24).sum()) / AIR_STEPS
+            out["write_bwd"] += float((4 * (O_w + Fw + S_w) + 48).sum()) / AIR_STEPS
+        return out
+
+
+def e2e_measure(a, dev, steps, warmup):
+    """Same 16*B glimpses per step, host (pinned) arrays in and out through mog_stn_fwd_bwd_host."""
+    import torch
+    from mog_asr_b200 import synth
+    from mog_asr_b200.host_api import HostSampler
+    B, cs, gs = a.batch, a.canvas, a.glimpse
+    pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
+    U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, gs, gs, 1), pin(B, cs, cs, 1)
+    rng = np.random.default_rng(10)
+    for t in (U_h, W_h):
+        t.copy_(torch.from_numpy(rng.random(tuple(t.shape), dtype=np.float32)))
+    for t in (g_r, g_w):
+        t.copy_(torch.from_numpy(rng.standard_normal(tuple(t.shape), dtype=np.float32)))
+    gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
+    th_r, th_w = [], []
+    for t in range(AIR_STEPS):
+        s, x, y = gen(B, seed=100 + t)
+        th_r.append(torch.from_numpy(synth.theta_read(s, x, y)).pin_memory())
+        th_w.append(torch.from_numpy(synth.theta_write(s, x, y)).pin_memory())
+    out_r, dU_r, out_w, dU_w, dth = pin(B, gs, gs, 1), pin(B, cs, cs, 1), pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, 6)
+    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(256, min(2048, B // 8)))
+    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=max(256, min(2048, B // 8)))
+
+    def step():
+        for t in range(AIR_STEPS):
+            rd.fwd_bwd(U_h, th_r[t], g_r, out=out_r, dU=dU_r, dtheta=dth)
+            wr.fwd_bwd(W_h, th_w[t], g_w, out=out_w, dU=dU_w, dtheta=dth)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    fl = 4
+    h2d = AIR_STEPS * fl * (U_h.numel() + g_r.numel() + W_h.numel() + g_w.numel() + 12 * B)
+    d2h = AIR_STEPS * fl * (out_r.numel() + dU_r.numel() + out_w.numel() + dU_w.numel() + 12 * B)
+    chunks = -(-B // rd.chunk)
+    return dt, h2d, d2h, AIR_STEPS * 2 * 2 * chunks
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this path has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mog_asr_b200 as M  # noqa: F401
+    from mog_asr_b200 import _lib
+    _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = GpuWorkload(a, dev, seed=10 + rank)
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        wl.step()
+    barrier()
+    events = {k: [] for k in wl.kinds}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tc0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        wl.step(events)
+    e1.record()
+    barrier()
+    tc1 = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / a.steps
+    glimpses_per_step = a.batch * 2 * AIR_STEPS * world
+    value = glimpses_per_step / (ms_per_step * 1e-3)
+
+    kern_ms = {k: float(np.mean([x.elapsed_time(y) for x, y in events[k]])) for k in wl.kinds}
+    kern_share = {k: kern_ms[k] * AIR_STEPS / ms_per_step for k in wl.kinds}
+
+    # e2e: host buffers through the C ABI
+    e2e = None
+    e2e_launches = 0
+    if not a.no_e2e:
+        e_steps = max(2, a.steps // 10)
+        dt, h2d, d2h, e2e_launches = e2e_measure(a, dev, e_steps, 1)
+        barrier()
+        dt = max_over_ranks(dt)
+        e2e = dict(value=glimpses_per_step / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                   ms_per_step=dt * 1e3, steps=e_steps,
+                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams)")
+    tc2 = time.perf_counter()
+    sampler.stop_flag = True
+    clocks = sampler.summary(tc0, tc2 if e2e else tc1)
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        abytes = wl.algorithmic_bytes()
+        dom = max(wl.kinds, key=lambda k: kern_ms[k])
+        kernels = {k: dict(ms=kern_ms[k], share_of_step=kern_share[k], alg_bytes_per_launch=abytes[k],
+                           achieved_gbs=abytes[k] / (kern_ms[k] * 1e-3) / 1e9,
+                           frac=abytes[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds}
+        sym = dict(read_fwd="stn_fwd_kernel<false>", write_fwd="stn_fwd_kernel<false>",
+                   read_bwd="stn_bwd_kernel<false,true>", write_bwd="stn_bwd_kernel<false,true>")
+        roofline = dict(bound="hbm", kernel=f"{sym[dom]} ({dom})", achieved=kernels[dom]["achieved_gbs"], peak=peak,
+                        unit="GB/s", frac=kernels[dom]["frac"], traffic=None, peak_source=peak_src,
+                        step_alg_gbs=sum(abytes.values()) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9 * 1.0,
+                        kernels=kernels)
+        roofline["step_frac"] = roofline["step_alg_gbs"] / peak
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic",
+                    config=dict(workload=workload_name(a), l2="inputs larger than L2 (per-call working set "
+                                f"{(wl.U.numel() * 2 + wl.out_r.numel() * 2) * 4 / 1e6:.0f} MB vs 126 MB L2); no flush",
+                                timing="CUDA events on the launch stream, max over ranks"),
+                    roofline=roofline, clocks=clocks, gpu_launches=4 * AIR_STEPS * a.steps)
+        if e2e:
+            line["e2e"] = e2e
+            line["e2e_gpu_launches"] = e2e_launches * e2e["steps"]
+        if world == 1 and not a.no_cpu:
+            cb, _ = cpu_measure(a, 3, 1, a.cpu_sample)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

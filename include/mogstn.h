@@ -1,0 +1,127 @@
+/* mogstn.h -- C ABI of libmogstn.so: the B200 (sm_100a) implementation of the MOG-ASR hot path.
+ *
+ * The reference (taufikxu/MOG-ASR) is pure Python on TensorFlow 1.12 and has no FFI of its own; the
+ * entry points below are what a binding for its hot path would need, one per reference interface:
+ *
+ *   mog_stn_forward            <- transformer(U, theta, out_size)          air/transformer.py:18,173-175
+ *                                 batch_transformer(U, thetas, out_size)   air/transformer.py:178-195 (u_batch_div = T)
+ *   mog_stn_backward           <- TF autodiff of that graph                air/air_number_bbox_location.py:1098
+ *   mog_stn_corners            <- the clipped corner indices x0,x1,y0,y1   air/transformer.py:79-87 (parity probe)
+ *   mog_stn_write_composite_*  <- write call site + canvas compositing     air/air_number_bbox_location.py:592-600,:718-727
+ *   mog_asr_reg_*              <- ASR regularisers                         air/air_number_bbox_location.py:645-681,:970-1069
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer to fp32 (or int32 where stated), dense row-major, owned by the
+ *     caller.  The library allocates nothing, keeps no state, never synchronises: each call enqueues
+ *     its kernels on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and returns.
+ *     All calls are CUDA-graph capturable and re-entrant.
+ *   - Layout is the reference's NHWC: U[B][Hs][Ws][C], out[B][Ho][Wo][C], theta[B][6] (= [B][2][3]).
+ *   - Return value: 0 on success; a negative mog_status on bad arguments; a positive cudaError_t value
+ *     if a launch failed.  Nothing is thrown across the ABI.  mog_last_error_string() describes the
+ *     last failure on the calling thread.
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef MOGSTN_H_
+#define MOGSTN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MOG_API __attribute__((visibility("default")))
+#else
+#define MOG_API
+#endif
+
+typedef enum {
+    MOG_OK = 0,
+    MOG_ERR_NULL = -1,        /* a required pointer is NULL */
+    MOG_ERR_DIM = -2,         /* non-positive or inconsistent dimension */
+    MOG_ERR_OVERFLOW = -3,    /* an element count does not fit the index type used (reference: silent int32 wrap) */
+    MOG_ERR_UNSUPPORTED = -4  /* shape outside what the kernels are built for (see message) */
+} mog_status;
+
+MOG_API int mog_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf; returns its full length. */
+MOG_API int mog_last_error_string(char* buf, size_t n);
+
+/* out[b] = bilinear_sample(U[b / u_batch_div]; theta[b])       (transformer.py:56-171)
+ * B counts thetas/outputs; U holds B / u_batch_div images (u_batch_div >= 1 must divide B). */
+MOG_API int mog_stn_forward(const float* U, const float* theta, float* out, int64_t B, int Hs, int Ws, int C, int Ho,
+                    int Wo, int u_batch_div, void* stream);
+
+/* corners: int32 [4][B*Ho*Wo] in the order x0, x1, y0, y1 after clipping (transformer.py:79-87). */
+MOG_API int mog_stn_corners(const float* theta, int32_t* corners, int64_t B, int Hs, int Ws, int Ho, int Wo,
+                    void* stream);
+
+/* Gradients of sum(gout * out).  dU (nullable) is [B / u_batch_div][Hs][Ws][C] and is fully overwritten
+ * (no pre-zeroing needed); dtheta (nullable) is [B][6] and fully overwritten. */
+MOG_API int mog_stn_backward(const float* U, const float* theta, const float* gout, float* dU, float* dtheta,
+                     int64_t B, int Hs, int Ws, int C, int Ho, int Wo, int u_batch_div, void* stream);
+
+/* Host-buffer form of forward + backward in one call (what one `sess.run([out, grads], feed_dict)` of
+ * the reference does, train_air_pr.py:294-295): U_h, theta_h, gout_h, out_h, dU_h (nullable), dtheta_h
+ * (nullable) are HOST pointers (pinned memory for full PCIe rate); the batch is cut into chunks that are
+ * copied in, sampled, differentiated and copied out on `nstreams` CUDA streams so H2D, kernels and D2H
+ * overlap.  workspace_d is caller-owned device scratch of at least mog_stn_host_workspace_bytes(...)
+ * bytes.  Unlike the device entry points this one waits for its streams before returning. */
+MOG_API int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, const float* gout_h, float* out_h, float* dU_h,
+                         float* dtheta_h, int64_t B, int Hs, int Ws, int C, int Ho, int Wo, int64_t chunk,
+                         void* workspace_d, size_t workspace_bytes, void* const* streams, int nstreams);
+/* Scratch needed by mog_stn_fwd_bwd_host for a given chunk size and stream count (returns 0 on bad args). */
+MOG_API size_t mog_stn_host_workspace_bytes(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo, int nstreams);
+
+/* canvas_out[b] = canvas_in[b] + (stop_sum[b] < threshold ? z_pres[b] * sample(U[b]; theta[b]) : 0)
+ * U is the [B][Hw][Ww] window (C = 1), canvases are [B][Hc][Wc]; canvas_out may alias canvas_in (the
+ * in-place form touches only pixels that change).  stop_sum NULL = every image active. */
+MOG_API int mog_stn_write_composite_forward(const float* U, const float* theta, const float* z_pres,
+                                    const float* stop_sum, float threshold, const float* canvas_in,
+                                    float* canvas_out, int64_t B, int Hw, int Ww, int Hc, int Wc, void* stream);
+
+/* Given gcanvas = d loss / d canvas_out: dU [B][Hw][Ww], dtheta [B][6], dz [B] (each nullable, each fully
+ * overwritten).  d loss / d canvas_in is gcanvas itself and is not written. */
+MOG_API int mog_stn_write_composite_backward(const float* U, const float* theta, const float* z_pres,
+                                     const float* stop_sum, float threshold, const float* gcanvas, float* dU,
+                                     float* dtheta, float* dz, int64_t B, int Hw, int Ww, int Hc, int Wc,
+                                     void* stream);
+
+/* ---- ASR regularisers (one fused per-image kernel) ------------------------------------------------ */
+#define MOG_ASR_MAX_STEPS 16
+#define MOG_ASR_MAX_COUNTS 8
+#define MOG_ASR_NUM_COMPONENTS 6 /* pr_num, num_min, area, out, size, overlap  (the reference's log_variables) */
+
+typedef struct {
+    float canvas_size;                  /* cs */
+    int max_steps;                      /* reference max_steps (columns of the objective) */
+    int num_counts;                     /* K = len(-dn) */
+    int counts[MOG_ASR_MAX_COUNTS];     /* c_k */
+    float gamma_num, gamma_margin, gamma_elem, gamma_bbox, gamma_size, gamma_area; /* -gn -gm -gne -gb -gs -ga */
+    float size_min, size_max;           /* constrains_area_minmax */
+} mog_asr_config;
+
+/* psum[t] += sum_b sigmoid(log_odds[b][t]); caller zeroes psum[T] first (and all-reduces it across ranks
+ * for global-batch semantics, air_number_bbox_location.py:982). */
+MOG_API int mog_asr_reg_colsum(const float* log_odds, float* psum, int64_t B, int T, void* stream);
+
+/* per_image[b] = pr_loss[b] + L_elem[b]; components [B][6] nullable; margin[1] = L_margin computed from
+ * psum * inv_global_batch.  log_odds [B][T], shifts [B][T][2], scales [B][T]. */
+MOG_API int mog_asr_reg_forward(const float* log_odds, const float* shifts, const float* scales, const float* psum,
+                        float inv_global_batch, int64_t B, int T, const mog_asr_config* cfg, float* per_image,
+                        float* components, float* margin, void* stream);
+
+/* Gradients of sum_b g_per_image[b]*per_image[b] + g_margin[0]*margin. */
+MOG_API int mog_asr_reg_backward(const float* log_odds, const float* shifts, const float* scales, const float* psum,
+                         float inv_global_batch, const float* g_per_image, const float* g_margin, int64_t B,
+                         int T, const mog_asr_config* cfg, float* d_log_odds, float* d_shifts, float* d_scales,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOGSTN_H_ */

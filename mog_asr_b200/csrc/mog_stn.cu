@@ -1,0 +1,537 @@
+// libmogstn -- spatial-transformer sampler of MOG-ASR for B200 (sm_100a).
+//
+// Replaces the ~70-op TensorFlow graph of /root/reference/air/transformer.py:18-175 (forward) and its
+// autodiff (backward) with one kernel each, plus the fused write+composite of
+// air/air_number_bbox_location.py:592-600,:718-727.  HBM-bound gather/scatter work: no tensor cores.
+//
+// Numerical contract (oracle/stn_ref_numpy.py): corner indices bit-exact; forward values computed with
+// the reference's operation order, one fp32 rounding per op (explicit _rn intrinsics, no FMA), so they
+// are bit-exact for finite inputs too.  Gradients are fp32 with a different (tree) summation order.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "mog_common.cuh"
+
+namespace mog {
+
+// ---------------------------------------------------------------------------------------------------
+// host-side plumbing
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+struct FwdArgs {
+    const float* U;
+    const float* theta;
+    float* out;
+    // composite only
+    const float* z_pres;
+    const float* stop_sum;
+    const float* canvas_in;
+    float threshold;
+    long long B;
+    int u_div;
+    Geo g;
+};
+
+// One CTA per output image (grid-stride).  Separable thetas (every AIR call site) use per-column /
+// per-row tables in shared memory so the per-pixel work is 2 LDS.128 + 4 gathers + 11 flops.
+template <bool COMPOSITE>
+__global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const FwdArgs a) {
+    extern __shared__ int4 s_tab[];  // [Wo] column entries, [Ho] row entries
+    const Geo& g = a.g;
+    const int C = g.C;
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        Theta th;
+        th.load(a.theta + 6 * b);
+        const bool sep = th.separable();
+        float z = 1.0f;
+        bool active = true;
+        if (COMPOSITE) {
+            z = __ldg(a.z_pres + b);
+            active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
+        }
+        const float* __restrict__ Ub = a.U + (b / a.u_div) * (long long)g.S * C;
+        float* __restrict__ ob = a.out + b * (long long)g.N * C;
+        const float* __restrict__ cb = COMPOSITE ? a.canvas_in + b * (long long)g.N : nullptr;
+        const bool inplace = COMPOSITE && (a.canvas_in == a.out);
+
+        if (COMPOSITE && !active) {
+            // where(mask, ., 0): canvas + 0  (air_number_bbox_location.py:722-727)
+            if (!inplace)
+                for (int n = threadIdx.x; n < g.N; n += kThreads) ob[n] = __fadd_rn(cb[n], 0.0f);
+            continue;
+        }
+        if (sep) {
+            __syncthreads();  // previous image's readers are done with the tables
+            build_tables(s_tab, th, g);
+            __syncthreads();
+        }
+        for (int n = threadIdx.x; n < g.N; n += kThreads) {
+            int i, j;
+            split_n(g, n, i, j);
+            int x0, x1, r0, r1;
+            float ax, bx, ay, by;
+            if (sep) {
+                const int4 cx = s_tab[j], cy = s_tab[g.Wo + i];
+                x0 = cx.x; x1 = cx.y; ax = __int_as_float(cx.z); bx = __int_as_float(cx.w);
+                r0 = cy.x; r1 = cy.y; ay = __int_as_float(cy.z); by = __int_as_float(cy.w);
+            } else {
+                Axis X, Y;
+                taps_general(th, g, i, j, X, Y);
+                x0 = X.c0; x1 = X.c1; ax = X.a; bx = X.b;
+                r0 = Y.c0 * g.Ws; r1 = Y.c1 * g.Ws; ay = Y.a; by = Y.b;
+            }
+            if (r0 == r1) {
+                // y out of range: both row taps alias one row and the weights pair up as +w/-w in add_n
+                // order, so the reference's result is exactly +0 for finite inputs (DESIGN.md "borders").
+                if (COMPOSITE) {
+                    if (!inplace) ob[n] = __fadd_rn(cb[n], 0.0f);
+                } else {
+                    for (int c = 0; c < C; ++c) ob[(long long)n * C + c] = 0.0f;
+                }
+                continue;
+            }
+            // transformer.py:112-115
+            const float wa = __fmul_rn(ax, ay), wb = __fmul_rn(ax, by), wc = __fmul_rn(bx, ay), wd = __fmul_rn(bx, by);
+            const float* pa = Ub + (long long)(r0 + x0) * C;
+            const float* pb = Ub + (long long)(r1 + x0) * C;
+            const float* pc = Ub + (long long)(r0 + x1) * C;
+            const float* pd = Ub + (long long)(r1 + x1) * C;
+            for (int c = 0; c < C; ++c) {
+                // transformer.py:116  add_n in list order
+                float v = __fadd_rn(__fmul_rn(wa, __ldg(pa + c)), __fmul_rn(wb, __ldg(pb + c)));
+                v = __fadd_rn(v, __fmul_rn(wc, __ldg(pc + c)));
+                v = __fadd_rn(v, __fmul_rn(wd, __ldg(pd + c)));
+                if (COMPOSITE)
+                    ob[n] = __fadd_rn(cb[n], __fmul_rn(z, v));  // :724-726
+                else
+                    ob[(long long)n * C + c] = v;
+            }
+        }
+    }
+}
+
+// corner probe: same evaluation paths as the forward kernel (tables for separable thetas)
+__global__ void __launch_bounds__(kThreads) stn_corners_kernel(const float* theta, int32_t* corners, long long B,
+                                                                const Geo g) {
+    extern __shared__ int4 s_tab[];
+    const long long BN = B * (long long)g.N;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        Theta th;
+        th.load(theta + 6 * b);
+        const bool sep = th.separable();
+        if (sep) {
+            __syncthreads();
+            build_tables(s_tab, th, g);
+            __syncthreads();
+        }
+        for (int n = threadIdx.x; n < g.N; n += kThreads) {
+            int i, j;
+            split_n(g, n, i, j);
+            int x0, x1, y0, y1;
+            if (sep) {
+                const int4 cx = s_tab[j], cy = s_tab[g.Wo + i];
+                x0 = cx.x; x1 = cx.y; y0 = cy.x / g.Ws; y1 = cy.y / g.Ws;
+            } else {
+                Axis X, Y;
+                taps_general(th, g, i, j, X, Y);
+                x0 = X.c0; x1 = X.c1; y0 = Y.c0; y1 = Y.c1;
+            }
+            const long long o = b * g.N + n;
+            corners[o] = x0;
+            corners[BN + o] = x1;
+            corners[2 * BN + o] = y0;
+            corners[3 * BN + o] = y1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward, general path: scatter-add of dU (shared-memory accumulation tile when the source image
+// fits, L2 atomics otherwise) + dtheta by warp shuffles then a block reduction.
+// One CTA per SOURCE image (all u_div transforms of it), so dU needs no inter-CTA atomics and no
+// separate zero-fill pass: the CTA writes every element of dU[bs] exactly once (tile flush) or zero-fills
+// then REDs while the lines are still L2-resident.
+// ---------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    const float* U;
+    const float* theta;
+    const float* gout;
+    float* dU;
+    float* dtheta;
+    // composite only
+    const float* z_pres;
+    const float* stop_sum;
+    float* dz;
+    float threshold;
+    long long Bsrc;
+    int u_div;
+    Geo g;
+};
+
+template <bool COMPOSITE, bool SMEM_ACC>
+__global__ void __launch_bounds__(kThreads) stn_bwd_kernel(const BwdArgs a) {
+    extern __shared__ int4 s_dyn[];
+    const Geo& g = a.g;
+    const int C = g.C;
+    int4* s_tab = s_dyn;                                                      // [Wo + Ho]
+    float* s_red = reinterpret_cast<float*>(s_dyn + g.Wo + g.Ho);             // [kWarps][8]
+    float* s_acc = s_red + kWarps * 8;                                        // [S*C] when SMEM_ACC
+    const int SC = g.S * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (long long bs = blockIdx.x; bs < a.Bsrc; bs += gridDim.x) {
+        const float* __restrict__ Ub = a.U + bs * (long long)SC;
+        float* __restrict__ dUb = a.dU ? a.dU + bs * (long long)SC : nullptr;
+        if (dUb) {
+            if (SMEM_ACC) {
+                for (int k = threadIdx.x; k < SC; k += kThreads) s_acc[k] = 0.0f;
+            } else {
+                for (int k = threadIdx.x; k < SC; k += kThreads) dUb[k] = 0.0f;
+            }
+        }
+        for (int t = 0; t < a.u_div; ++t) {
+            const long long b = bs * a.u_div + t;
+            Theta th;
+            th.load(a.theta + 6 * b);
+            const bool sep = th.separable();
+            float z = 1.0f;
+            bool active = true;
+            if (COMPOSITE) {
+                z = __ldg(a.z_pres + b);
+                active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
+            }
+            __syncthreads();  // tables/s_red free, zero-fill visible
+            if (sep && active) build_tables(s_tab, th, g);
+            __syncthreads();
+            float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                const float* __restrict__ gb = a.gout + b * (long long)g.N * C;
+                for (int n = threadIdx.x; n < g.N; n += kThreads) {
+                    int i, j;
+                    split_n(g, n, i, j);
+                    int x0, x1, r0, r1;
+                    float ax, bx, ay, by;
+                    if (sep) {
+                        const int4 cx = s_tab[j], cy = s_tab[g.Wo + i];
+                        x0 = cx.x; x1 = cx.y; ax = __int_as_float(cx.z); bx = __int_as_float(cx.w);
+                        r0 = cy.x; r1 = cy.y; ay = __int_as_float(cy.z); by = __int_as_float(cy.w);
+                    } else {
+                        Axis X, Y;
+                        taps_general(th, g, i, j, X, Y);
+                        x0 = X.c0; x1 = X.c1; ax = X.a; bx = X.b;
+                        r0 = Y.c0 * g.Ws; r1 = Y.c1 * g.Ws; ay = Y.a; by = Y.b;
+                    }
+                    // Out of range on an axis: the two taps alias one pixel with weights +w/-w, so every
+                    // gradient contribution cancels in exact arithmetic (DESIGN.md "borders").
+                    if (x0 == x1 || r0 == r1) continue;
+                    const int ia = (r0 + x0) * C, ib = (r1 + x0) * C, ic = (r0 + x1) * C, id = (r1 + x1) * C;
+                    const float wa = ax * ay, wb = ax * by, wc = bx * ay, wd = bx * by;
+                    float sx = 0.f, sy = 0.f;  // sum_c g*[ay(Ic-Ia)+by(Id-Ib)],  sum_c g*[ax(Ib-Ia)+bx(Id-Ic)]
+                    for (int c = 0; c < C; ++c) {
+                        const float gc = __ldg(gb + (long long)n * C + c);
+                        const float gv = COMPOSITE ? gc * z : gc;
+                        const float Ia = __ldg(Ub + ia + c), Ib = __ldg(Ub + ib + c);
+                        const float Ic = __ldg(Ub + ic + c), Id = __ldg(Ub + id + c);
+                        if (dUb) {
+                            float* acc = SMEM_ACC ? s_acc : dUb;
+                            atomicAdd(acc + ia + c, wa * gv);
+                            atomicAdd(acc + ib + c, wb * gv);
+                            atomicAdd(acc + ic + c, wc * gv);
+                            atomicAdd(acc + id + c, wd * gv);
+                        }
+                        sx += gv * (ay * (Ic - Ia) + by * (Id - Ib));
+                        sy += gv * (ax * (Ib - Ia) + bx * (Id - Ic));
+                        if (COMPOSITE) p[6] += gc * (wa * Ia + wb * Ib + wc * Ic + wd * Id);
+                    }
+                    const float dxs = sx * g.wsc * 0.5f, dys = sy * g.hsc * 0.5f;
+                    const float xt = lin_at(j, g.step_w), yt = lin_at(i, g.step_h);
+                    p[0] += dxs * xt; p[1] += dxs * yt; p[2] += dxs;
+                    p[3] += dys * xt; p[4] += dys * yt; p[5] += dys;
+                }
+            }
+            // dtheta / dz: warp shuffles, then a block reduction through shared memory
+#pragma unroll
+            for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) s_red[warp * 8 + k] = p[k];
+            }
+            __syncthreads();
+            if (threadIdx.x < 7) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) v += s_red[w * 8 + threadIdx.x];
+                if (threadIdx.x < 6) {
+                    if (a.dtheta) a.dtheta[6 * b + threadIdx.x] = v;
+                } else if (COMPOSITE && a.dz) {
+                    a.dz[b] = v;
+                }
+            }
+        }
+        if (dUb && SMEM_ACC) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < SC; k += kThreads) dUb[k] = s_acc[k];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------
+static int check_dims(long long B, int Hs, int Ws, int C, int Ho, int Wo, int u_div) {
+    MOG_REQUIRE(B >= 0 && Hs > 0 && Ws > 0 && C > 0 && Ho > 0 && Wo > 0, MOG_ERR_DIM,
+                "non-positive dimension: B=%lld Hs=%d Ws=%d C=%d Ho=%d Wo=%d", B, Hs, Ws, C, Ho, Wo);
+    MOG_REQUIRE(u_div >= 1 && B % u_div == 0, MOG_ERR_DIM, "u_batch_div=%d must be >= 1 and divide B=%lld", u_div, B);
+    MOG_REQUIRE((long long)Hs * Ws * C < (1ll << 30) && (long long)Ho * Wo * C < (1ll << 30), MOG_ERR_OVERFLOW,
+                "per-image element count exceeds 2^30 (Hs*Ws*C=%lld, Ho*Wo*C=%lld)", (long long)Hs * Ws * C,
+                (long long)Ho * Wo * C);
+    MOG_REQUIRE((unsigned long long)Ho * Wo * (unsigned long long)Wo < (1ull << 32), MOG_ERR_UNSUPPORTED,
+                "Ho*Wo*Wo must be < 2^32 for the index split (Ho=%d Wo=%d)", Ho, Wo);
+    MOG_REQUIRE((size_t)(Ho + Wo) * sizeof(int4) <= 64 * 1024, MOG_ERR_UNSUPPORTED, "Ho+Wo=%d too large for the axis tables",
+                Ho + Wo);
+    return MOG_OK;
+}
+
+static int grid_for(long long units, int ctas_per_sm) {
+    const long long cap = (long long)sm_count() * ctas_per_sm;
+    return (int)(units < cap ? (units > 0 ? units : 1) : cap);
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(%zu B dynamic smem): %s", bytes, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    return 0;
+}
+
+template <bool COMPOSITE>
+static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+    if (a.B == 0) return MOG_OK;
+    const size_t smem = (size_t)(a.g.Wo + a.g.Ho) * sizeof(int4);
+    if (int rc = set_smem(stn_fwd_kernel<COMPOSITE>, smem)) return rc;
+    stn_fwd_kernel<COMPOSITE><<<grid_for(a.B, 8), kThreads, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_fwd_kernel");
+    return MOG_OK;
+}
+
+template <bool COMPOSITE>
+static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+    if (a.Bsrc == 0) return MOG_OK;
+    const size_t base = (size_t)(a.g.Wo + a.g.Ho) * sizeof(int4) + kWarps * 8 * sizeof(float);
+    const size_t tile = a.dU ? (size_t)a.g.S * a.g.C * sizeof(float) : 0;
+    const bool smem_acc = a.dU && base + tile <= (size_t)kMaxSmemBytes;
+    const size_t smem = base + (smem_acc ? tile : 0);
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const int grid = grid_for(a.Bsrc, per_sm);
+    if (smem_acc) {
+        if (int rc = set_smem(stn_bwd_kernel<COMPOSITE, true>, smem)) return rc;
+        stn_bwd_kernel<COMPOSITE, true><<<grid, kThreads, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(stn_bwd_kernel<COMPOSITE, false>, smem)) return rc;
+        stn_bwd_kernel<COMPOSITE, false><<<grid, kThreads, smem, st>>>(a);
+    }
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_kernel");
+    return MOG_OK;
+}
+
+}  // namespace mog
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+using namespace mog;
+
+extern "C" int mog_version(void) { return MOG_ABI_VERSION; }
+
+extern "C" int mog_last_error_string(char* buf, size_t n) {
+    const size_t len = strlen(g_err);
+    if (buf && n) {
+        const size_t k = len < n - 1 ? len : n - 1;
+        memcpy(buf, g_err, k);
+        buf[k] = 0;
+    }
+    return (int)len;
+}
+
+extern "C" int mog_stn_forward(const float* U, const float* theta, float* out, int64_t B, int Hs, int Ws, int C,
+                               int Ho, int Wo, int u_batch_div, void* stream) {
+    if (int rc = check_dims(B, Hs, Ws, C, Ho, Wo, u_batch_div)) return rc;
+    MOG_REQUIRE(B == 0 || (U && theta && out), MOG_ERR_NULL, "mog_stn_forward: NULL pointer (U=%p theta=%p out=%p)", (const void*)U,
+                (const void*)theta, (void*)out);
+    FwdArgs a{};
+    a.U = U; a.theta = theta; a.out = out; a.B = B; a.u_div = u_batch_div;
+    a.g = make_geo(Hs, Ws, C, Ho, Wo);
+    return launch_fwd<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_corners(const float* theta, int32_t* corners, int64_t B, int Hs, int Ws, int Ho, int Wo,
+                               void* stream) {
+    if (int rc = check_dims(B, Hs, Ws, 1, Ho, Wo, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (theta && corners), MOG_ERR_NULL, "mog_stn_corners: NULL pointer");
+    if (B == 0) return MOG_OK;
+    const Geo g = make_geo(Hs, Ws, 1, Ho, Wo);
+    const size_t smem = (size_t)(Wo + Ho) * sizeof(int4);
+    if (int rc = set_smem(stn_corners_kernel, smem)) return rc;
+    stn_corners_kernel<<<grid_for(B, 8), kThreads, smem, (cudaStream_t)stream>>>(theta, corners, B, g);
+    MOG_CUDA_LAUNCH_CHECK("stn_corners_kernel");
+    return MOG_OK;
+}
+
+extern "C" int mog_stn_backward(const float* U, const float* theta, const float* gout, float* dU, float* dtheta,
+                                int64_t B, int Hs, int Ws, int C, int Ho, int Wo, int u_batch_div, void* stream) {
+    if (int rc = check_dims(B, Hs, Ws, C, Ho, Wo, u_batch_div)) return rc;
+    MOG_REQUIRE(B == 0 || (U && theta && gout), MOG_ERR_NULL, "mog_stn_backward: NULL pointer (U=%p theta=%p gout=%p)",
+                (const void*)U, (const void*)theta, (const void*)gout);
+    if (!dU && !dtheta) return MOG_OK;
+    BwdArgs a{};
+    a.U = U; a.theta = theta; a.gout = gout; a.dU = dU; a.dtheta = dtheta;
+    a.Bsrc = B / u_batch_div; a.u_div = u_batch_div;
+    a.g = make_geo(Hs, Ws, C, Ho, Wo);
+    return launch_bwd<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_write_composite_forward(const float* U, const float* theta, const float* z_pres,
+                                               const float* stop_sum, float threshold, const float* canvas_in,
+                                               float* canvas_out, int64_t B, int Hw, int Ww, int Hc, int Wc,
+                                               void* stream) {
+    if (int rc = check_dims(B, Hw, Ww, 1, Hc, Wc, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && theta && z_pres && canvas_in && canvas_out), MOG_ERR_NULL,
+                "mog_stn_write_composite_forward: NULL pointer");
+    FwdArgs a{};
+    a.U = U; a.theta = theta; a.out = canvas_out; a.z_pres = z_pres; a.stop_sum = stop_sum; a.canvas_in = canvas_in;
+    a.threshold = threshold; a.B = B; a.u_div = 1;
+    a.g = make_geo(Hw, Ww, 1, Hc, Wc);
+    return launch_fwd<true>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_write_composite_backward(const float* U, const float* theta, const float* z_pres,
+                                                const float* stop_sum, float threshold, const float* gcanvas,
+                                                float* dU, float* dtheta, float* dz, int64_t B, int Hw, int Ww,
+                                                int Hc, int Wc, void* stream) {
+    if (int rc = check_dims(B, Hw, Ww, 1, Hc, Wc, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && theta && z_pres && gcanvas), MOG_ERR_NULL, "mog_stn_write_composite_backward: NULL pointer");
+    if (!dU && !dtheta && !dz) return MOG_OK;
+    BwdArgs a{};
+    a.U = U; a.theta = theta; a.gout = gcanvas; a.dU = dU; a.dtheta = dtheta; a.z_pres = z_pres;
+    a.stop_sum = stop_sum; a.dz = dz; a.threshold = threshold; a.Bsrc = B; a.u_div = 1;
+    a.g = make_geo(Hw, Ww, 1, Hc, Wc);
+    return launch_bwd<true>(a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-buffer entry point (the end-to-end path): chunked H2D -> forward -> backward -> D2H on several streams
+// ---------------------------------------------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct HostChunkLayout {
+    size_t U, theta, gout, out, dU, dtheta, total;
+};
+
+static HostChunkLayout host_chunk_layout(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo) {
+    HostChunkLayout l;
+    size_t o = 0;
+    l.U = o;      o += align256((size_t)chunk * Hs * Ws * C * sizeof(float));
+    l.theta = o;  o += align256((size_t)chunk * 6 * sizeof(float));
+    l.gout = o;   o += align256((size_t)chunk * Ho * Wo * C * sizeof(float));
+    l.out = o;    o += align256((size_t)chunk * Ho * Wo * C * sizeof(float));
+    l.dU = o;     o += align256((size_t)chunk * Hs * Ws * C * sizeof(float));
+    l.dtheta = o; o += align256((size_t)chunk * 6 * sizeof(float));
+    l.total = o;
+    return l;
+}
+
+extern "C" size_t mog_stn_host_workspace_bytes(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo, int nstreams) {
+    if (chunk <= 0 || Hs <= 0 || Ws <= 0 || C <= 0 || Ho <= 0 || Wo <= 0 || nstreams <= 0) return 0;
+    return host_chunk_layout(chunk, Hs, Ws, C, Ho, Wo).total * (size_t)nstreams;
+}
+
+#define MOG_CUDA_TRY(expr)                                                \
+    do {                                                                  \
+        cudaError_t e__ = (expr);                                         \
+        if (e__ != cudaSuccess) {                                         \
+            set_error("%s: %s", #expr, cudaGetErrorString(e__));          \
+            return (int)e__;                                              \
+        }                                                                 \
+    } while (0)
+
+extern "C" int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, const float* gout_h, float* out_h,
+                                    float* dU_h, float* dtheta_h, int64_t B, int Hs, int Ws, int C, int Ho, int Wo,
+                                    int64_t chunk, void* workspace_d, size_t workspace_bytes, void* const* streams,
+                                    int nstreams) {
+    if (int rc = check_dims(B, Hs, Ws, C, Ho, Wo, 1)) return rc;
+    MOG_REQUIRE(chunk > 0 && nstreams > 0 && nstreams <= 16, MOG_ERR_DIM, "fwd_bwd_host: chunk=%lld nstreams=%d", (long long)chunk, nstreams);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(U_h && theta_h && gout_h && out_h && workspace_d && streams, MOG_ERR_NULL, "fwd_bwd_host: NULL pointer");
+    const HostChunkLayout l = host_chunk_layout(chunk, Hs, Ws, C, Ho, Wo);
+    MOG_REQUIRE(workspace_bytes >= l.total * (size_t)nstreams, MOG_ERR_DIM, "fwd_bwd_host: workspace %zu B < required %zu B",
+                workspace_bytes, l.total * (size_t)nstreams);
+    const size_t imU = (size_t)Hs * Ws * C, imO = (size_t)Ho * Wo * C;
+    const Geo g = make_geo(Hs, Ws, C, Ho, Wo);
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
+        const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        cudaStream_t st = (cudaStream_t)streams[k % nstreams];
+        char* base = (char*)workspace_d + l.total * (size_t)(k % nstreams);
+        float* dUin = (float*)(base + l.U);
+        float* dth = (float*)(base + l.theta);
+        float* dgo = (float*)(base + l.gout);
+        float* dout = (float*)(base + l.out);
+        float* ddU = (float*)(base + l.dU);
+        float* ddth = (float*)(base + l.dtheta);
+        MOG_CUDA_TRY(cudaMemcpyAsync(dUin, U_h + b0 * imU, nb * imU * sizeof(float), cudaMemcpyHostToDevice, st));
+        MOG_CUDA_TRY(cudaMemcpyAsync(dth, theta_h + b0 * 6, nb * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+        MOG_CUDA_TRY(cudaMemcpyAsync(dgo, gout_h + b0 * imO, nb * imO * sizeof(float), cudaMemcpyHostToDevice, st));
+        FwdArgs fa{};
+        fa.U = dUin; fa.theta = dth; fa.out = dout; fa.B = nb; fa.u_div = 1; fa.g = g;
+        if (int rc = launch_fwd<false>(fa, st)) return rc;
+        MOG_CUDA_TRY(cudaMemcpyAsync(out_h + b0 * imO, dout, nb * imO * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (dU_h || dtheta_h) {
+            BwdArgs ba{};
+            ba.U = dUin; ba.theta = dth; ba.gout = dgo; ba.dU = dU_h ? ddU : nullptr; ba.dtheta = dtheta_h ? ddth : nullptr;
+            ba.Bsrc = nb; ba.u_div = 1; ba.g = g;
+            if (int rc = launch_bwd<false>(ba, st)) return rc;
+            if (dU_h)
+                MOG_CUDA_TRY(cudaMemcpyAsync(dU_h + b0 * imU, ddU, nb * imU * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (dtheta_h)
+                MOG_CUDA_TRY(cudaMemcpyAsync(dtheta_h + b0 * 6, ddth, nb * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    const int used = k < nstreams ? k : nstreams;
+    for (int i = 0; i < used; ++i) MOG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)streams[i]));
+    return MOG_OK;
+}

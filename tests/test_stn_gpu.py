@@ -1,0 +1,224 @@
+"""GPU parity tests of the sampler: CUDA path (through the C ABI) vs the oracle.
+
+Contract: corner indices bit-exact; forward values bit-exact for finite inputs (same operation order,
+no FMA) with the SURVEY A.1 bound as the documented tolerance; gradients within GRAD_RTOL of the fp64
+oracle relative to the sum of |terms| (atomic / tree order makes them non-bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+import mog_asr_b200 as M
+from mog_asr_b200 import synth
+from oracle import stn_ref_numpy as R
+from oracle import stn_ref_c as RC
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def run_fwd_bwd(dev, U, theta, out_size, gout, need_dU=True):
+    Ut = torch.tensor(U, device=dev, requires_grad=need_dU)
+    tt = torch.tensor(theta, device=dev, requires_grad=True)
+    out = M.transformer(Ut, tt, tuple(int(v) for v in out_size))
+    out.backward(torch.tensor(gout, device=dev))
+    torch.cuda.synchronize()
+    return (out.detach().cpu().numpy(), Ut.grad.cpu().numpy() if need_dU else None,
+            tt.grad.cpu().numpy().reshape(-1, 2, 3))
+
+
+@pytest.mark.parametrize("name", H.STN_CASES)
+def test_golden_forward_corners_backward(cuda_device, name):
+    d = H.load(name)
+    Hs, Ws = d["U"].shape[1:3]
+    corners = M.stn_corners(torch.tensor(d["theta"], device=cuda_device), (Hs, Ws), d["out_size"]).cpu().numpy()
+    assert np.array_equal(corners, d["corners"].reshape(corners.shape)), "corner indices must be bit-exact"
+    out, dU, dth = run_fwd_bwd(cuda_device, d["U"], d["theta"], d["out_size"], d["gout"])
+    # stated tolerance (always checked) ...
+    B, C = out.shape[0], d["U"].shape[-1]
+    bound = H.FWD_EPS_FACTOR * H.EPS32 * d["wsum"].reshape(B, -1, 1) * np.abs(d["U"]).max()
+    err = np.abs(out - d["out"]).reshape(B, -1, C)
+    fin = np.isfinite(d["out"]).reshape(B, -1, C)
+    assert np.all((err <= bound) | ~fin)
+    # ... and the stronger property the kernels are written for
+    assert H.same_bits_or_nan(out, d["out"]), "forward is expected to be bit-exact with the oracle"
+    assert H.grad_excess(dU, d["dU"], d["absdU"]) <= 1.0
+    assert H.grad_excess(dth, d["dtheta"], d["absdtheta"]) <= 1.0
+
+
+def test_dtheta_only_mode_matches_full_mode(cuda_device):
+    d = H.load("read_50_28")
+    _, _, dth_full = run_fwd_bwd(cuda_device, d["U"], d["theta"], d["out_size"], d["gout"], need_dU=True)
+    _, dU, dth_only = run_fwd_bwd(cuda_device, d["U"], d["theta"], d["out_size"], d["gout"], need_dU=False)
+    assert dU is None
+    assert np.array_equal(dth_full, dth_only)
+
+
+@pytest.mark.parametrize("Hs,Ho,direction", [(50, 28, "read"), (50, 28, "write"), (64, 28, "read"),
+                                              (64, 28, "write"), (128, 64, "read"), (256, 64, "read"),
+                                              (256, 64, "write"), (256, 28, "read")])
+@pytest.mark.parametrize("regime", ["prior", "full"])
+def test_seeded_parity_vs_c_oracle(cuda_device, Hs, Ho, direction, regime):
+    """Config-5 shapes at a batch the oracle finishes in seconds."""
+    B = 48 if Hs <= 64 else 12
+    rng = np.random.default_rng(Hs * 1000 + Ho)
+    s, x, y = (synth.sxy_prior_like if regime == "prior" else synth.sxy_full_cover)(B, seed=11)
+    if direction == "read":
+        U = rng.random((B, Hs, Hs, 1), dtype=np.float32)
+        th, out_size = synth.theta_read(s, x, y), (Ho, Ho)
+    else:
+        U = rng.random((B, Ho, Ho, 1), dtype=np.float32)
+        th, out_size = synth.theta_write(s, x, y), (Hs, Hs)
+    g = rng.normal(size=(B, out_size[0], out_size[1], 1)).astype(np.float32)
+    ref_out, ref_c = RC.forward(U, th, out_size, want_corners=True)
+    corners = M.stn_corners(torch.tensor(th, device=cuda_device), U.shape[1:3], out_size).cpu().numpy()
+    assert np.array_equal(corners, ref_c)
+    out, dU, dth = run_fwd_bwd(cuda_device, U, th, out_size, g)
+    assert H.same_bits_or_nan(out, ref_out)
+    dU64, dth64 = R.transformer_backward(U, th, out_size, g, dtype=np.float64)
+    aU, ath = R.backward_term_magnitudes(U, th, out_size, g)
+    assert H.grad_excess(dU, dU64, aU) <= 1.0
+    assert H.grad_excess(dth, dth64, ath) <= 1.0
+
+
+def test_general_affine_and_channels(cuda_device):
+    rng = np.random.default_rng(21)
+    B, Hs, Ws, C, Ho, Wo = 20, 37, 41, 4, 19, 23
+    U = rng.normal(size=(B, Hs, Ws, C)).astype(np.float32)
+    th = (np.tile(np.asarray([[0.8, 0, 0, 0, 0.8, 0]], np.float32), (B, 1)) + rng.normal(0, 0.3, (B, 6))).astype(np.float32)
+    g = rng.normal(size=(B, Ho, Wo, C)).astype(np.float32)
+    ref_out, ref_c = RC.forward(U, th, (Ho, Wo), want_corners=True)
+    assert np.array_equal(M.stn_corners(torch.tensor(th, device=cuda_device), (Hs, Ws), (Ho, Wo)).cpu().numpy(), ref_c)
+    out, dU, dth = run_fwd_bwd(cuda_device, U, th, (Ho, Wo), g)
+    assert H.same_bits_or_nan(out, ref_out)
+    dU64, dth64 = R.transformer_backward(U, th, (Ho, Wo), g, dtype=np.float64)
+    aU, ath = R.backward_term_magnitudes(U, th, (Ho, Wo), g)
+    assert H.grad_excess(dU, dU64, aU) <= 1.0
+    assert H.grad_excess(dth, dth64, ath) <= 1.0
+
+
+def test_batch_transformer_matches_repeat(cuda_device):
+    rng = np.random.default_rng(22)
+    B, T = 6, 8
+    U = rng.random((B, 50, 50, 1), dtype=np.float32)
+    s, x, y = synth.sxy_prior_like(B * T, seed=5)
+    th = synth.theta_read(s, x, y).reshape(B, T, 6)
+    g = rng.normal(size=(B * T, 28, 28, 1)).astype(np.float32)
+    Ut = torch.tensor(U, device=cuda_device, requires_grad=True)
+    tt = torch.tensor(th, device=cuda_device, requires_grad=True)
+    out = M.batch_transformer(Ut, tt, (28, 28))
+    assert out.shape == (B * T, 28, 28, 1)
+    out.backward(torch.tensor(g, device=cuda_device))
+    ref = R.batch_transformer(U, th, (28, 28))
+    assert H.same_bits_or_nan(out.detach().cpu().numpy(), ref)
+    Urep = np.repeat(U, T, axis=0)
+    dU64, dth64 = R.transformer_backward(Urep, th.reshape(-1, 6), (28, 28), g)
+    aU, ath = R.backward_term_magnitudes(Urep, th.reshape(-1, 6), (28, 28), g)
+    dU64 = dU64.reshape(B, T, 50, 50, 1).sum(1)
+    aU = aU.reshape(B, T, 50, 50, 1).sum(1)
+    assert H.grad_excess(Ut.grad.cpu().numpy(), dU64, aU) <= 1.0
+    assert H.grad_excess(tt.grad.cpu().numpy().reshape(-1, 2, 3), dth64, ath) <= 1.0
+
+
+def test_empty_and_ragged_inputs(cuda_device):
+    out = M.transformer(torch.zeros((0, 50, 50, 1), device=cuda_device), torch.zeros((0, 6), device=cuda_device), (28, 28))
+    assert out.shape == (0, 28, 28, 1)
+    # theta as [B,2,3], non-contiguous U, float64 inputs: cast/reshaped like transformer.py:101,144-145
+    rng = np.random.default_rng(3)
+    U = rng.random((5, 13, 50, 2))
+    th = rng.normal(0, 0.5, (5, 2, 3))
+    Ut = torch.tensor(U, device=cuda_device).transpose(1, 2)          # [5,50,13,2] view
+    out = M.transformer(Ut, torch.tensor(th, device=cuda_device), (7, 9))
+    ref = R.transformer(np.ascontiguousarray(U.transpose(0, 2, 1, 3)).astype(np.float32), th.astype(np.float32), (7, 9))
+    assert H.same_bits_or_nan(out.cpu().numpy(), ref)
+    with pytest.raises(ValueError):
+        M.transformer(torch.zeros((2, 5, 5, 1), device=cuda_device), torch.zeros((3, 6), device=cuda_device), (2, 2))
+
+
+def test_nan_theta_propagates_and_stays_in_bounds(cuda_device):
+    U = torch.ones((2, 9, 9, 1), device=cuda_device)
+    th = torch.tensor([[float("nan"), 0, 0, 0, 1, 0], [1, 0, 0, 0, float("inf"), 0]], device=cuda_device)
+    out = M.transformer(U, th, (5, 5))
+    torch.cuda.synchronize()
+    assert torch.isnan(out[0]).all()
+    c = M.stn_corners(th, (9, 9), (5, 5))
+    assert int(c.min()) >= 0 and int(c.max()) <= 8
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config-5 size (B = 16384) through size-independent properties: linearity in U and in
+    gout, zero gradient for out-of-range glimpses, determinism of the forward."""
+    B = 16384
+    g = torch.Generator(device=cuda_device).manual_seed(10)
+    U = torch.rand((B, 50, 50, 1), device=cuda_device, generator=g)
+    s, x, y = synth.sxy_prior_like(B, seed=1)
+    th = torch.tensor(synth.theta_read(s, x, y), device=cuda_device)
+    out1 = M.transformer(U, th, (28, 28))
+    out2 = M.transformer(U, th, (28, 28))
+    assert torch.equal(out1, out2)
+    # exact linearity under power-of-two scaling (every product/sum scales exactly)
+    assert torch.equal(M.transformer(U * 4.0, th, (28, 28)), out1 * 4.0)
+    # checksum of checksums against the C oracle on a strided sample of the batch
+    idx = torch.arange(0, B, 257, device=cuda_device)
+    ref = RC.forward(U[idx].cpu().numpy(), th[idx].cpu().numpy(), (28, 28))
+    assert H.same_bits_or_nan(out1[idx].cpu().numpy(), ref)
+    # gradients: linear in gout
+    Ug = U.clone().requires_grad_(True)
+    tg = th.clone().requires_grad_(True)
+    go = torch.randn((B, 28, 28, 1), device=cuda_device, generator=g)
+    o = M.transformer(Ug, tg, (28, 28))
+    dU1, dt1 = torch.autograd.grad(o, (Ug, tg), go, retain_graph=True)
+    dU2, dt2 = torch.autograd.grad(o, (Ug, tg), go * 2.0)
+    assert torch.allclose(dU2, dU1 * 2.0, rtol=1e-5, atol=1e-6) and torch.allclose(dt2, dt1 * 2.0, rtol=1e-4, atol=1e-4)
+    # sum(dU) == sum over in-range pixels of g (bilinear weights sum to 1): compare on the sample
+    dUs, dts = R.transformer_backward(U[idx].cpu().numpy(), th[idx].cpu().numpy(), (28, 28), go[idx].cpu().numpy())
+    aU, ath = R.backward_term_magnitudes(U[idx].cpu().numpy(), th[idx].cpu().numpy(), (28, 28), go[idx].cpu().numpy())
+    assert H.grad_excess(dU1[idx].cpu().numpy(), dUs, aU) <= 1.0
+    assert H.grad_excess(dt1[idx].cpu().numpy().reshape(-1, 2, 3), dts, ath) <= 1.0
+
+
+def test_composite_golden(cuda_device):
+    d = H.load("composite_28_50")
+    dev = cuda_device
+    canvas = torch.tensor(d["canvas"], device=dev, requires_grad=True)
+    U = torch.tensor(d["U"], device=dev, requires_grad=True)
+    th = torch.tensor(d["theta"], device=dev, requires_grad=True)
+    z = torch.tensor(d["z"], device=dev, requires_grad=True)
+    stop = torch.tensor(d["stop_sum"], device=dev)
+    out = M.write_composite(canvas, U, th, z, stop, float(d["threshold"]))
+    assert H.same_bits_or_nan(out.detach().cpu().numpy(), d["out"])
+    out.backward(torch.tensor(d["gcanvas"], device=dev))
+    assert np.array_equal(canvas.grad.cpu().numpy(), d["gcanvas"])
+    mask = d["stop_sum"] < d["threshold"]
+    gwin = (mask * d["z"])[:, None, None, None] * d["gcanvas"][..., None]
+    aU, ath = R.backward_term_magnitudes(d["U"][..., None], d["theta"], (50, 50), gwin)
+    assert H.grad_excess(U.grad.cpu().numpy()[..., None], d["dU"][..., None], aU) <= 1.0
+    assert H.grad_excess(th.grad.cpu().numpy().reshape(-1, 2, 3), d["dtheta"], ath) <= 1.0
+    win = R.transformer(d["U"][..., None], d["theta"], (50, 50))[..., 0]
+    az = (np.abs(d["gcanvas"]) * np.abs(win)).sum((1, 2))
+    assert H.grad_excess(z.grad.cpu().numpy(), d["dz"], az + 1e-3) <= 1.0
+    # in-place form gives the same canvas and leaves inactive images untouched
+    c2 = torch.tensor(d["canvas"], device=dev)
+    r = M.write_composite(c2, U.detach(), th.detach(), z.detach(), stop, float(d["threshold"]), inplace=True)
+    assert r.data_ptr() == c2.data_ptr()
+    assert H.same_bits_or_nan(c2.cpu().numpy(), d["out"])
+    # flat [B, cs*cs] canvases and windows like the reference's running_recon / vae_recon
+    r2 = M.write_composite(torch.tensor(d["canvas"], device=dev).reshape(8, -1), U.detach().reshape(8, -1),
+                           th.detach(), z.detach(), stop, float(d["threshold"]))
+    assert r2.shape == (8, 2500) and H.same_bits_or_nan(r2.cpu().numpy().reshape(8, 50, 50), d["out"])
+
+
+def test_composite_equals_unfused_ops(cuda_device):
+    """Fused kernel == transformer() followed by the reference's where/mul/add (air_number_bbox_location.py:722-727)."""
+    dev = cuda_device
+    B = 256
+    gen = torch.Generator(device=dev).manual_seed(2)
+    canvas = torch.rand((B, 64, 64), device=dev, generator=gen)
+    U = torch.sigmoid(torch.randn((B, 28, 28), device=dev, generator=gen))
+    s, x, y = synth.sxy_prior_like(B, seed=9)
+    th = torch.tensor(synth.theta_write(s, x, y), device=dev)
+    z = torch.rand(B, device=dev, generator=gen)
+    stop = torch.rand(B, device=dev, generator=gen) * 1.5
+    fused = M.write_composite(canvas, U, th, z, stop, 0.9)
+    win = M.transformer(U[..., None], th, (64, 64))[..., 0]
+    unfused = canvas + torch.where((stop < 0.9)[:, None, None], z[:, None, None] * win, torch.zeros_like(win))
+    assert torch.equal(fused, unfused)
