@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libmogstn.so")
 SOURCES = ["mog_stn.cu", "mog_asr.cu"]
-HEADERS = [os.path.join(CSRC, "mog_common.cuh"), os.path.join(ROOT, "include", "mogstn.h")]
+HEADERS = [os.path.join(CSRC, "mog_common.cuh"), os.path.join(CSRC, "mog_stn_warp.cuh"), os.path.join(ROOT, "include", "mogstn.h")]
 
 
 def nvcc_path() -> str:

@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "mog_common.cuh"
+#include "mog_stn_warp.cuh"
 
 namespace mog {
 
@@ -39,107 +40,10 @@ int sm_count() {
     return cached[dev];
 }
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
 
-// ---------------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------------
-struct FwdArgs {
-    const float* U;
-    const float* theta;
-    float* out;
-    // composite only
-    const float* z_pres;
-    const float* stop_sum;
-    const float* canvas_in;
-    float threshold;
-    long long B;
-    int u_div;
-    Geo g;
-};
-
-// One CTA per output image (grid-stride).  Separable thetas (every AIR call site) use per-column /
-// per-row tables in shared memory so the per-pixel work is 2 LDS.128 + 4 gathers + 11 flops.
-template <bool COMPOSITE>
-__global__ void __launch_bounds__(kThreads) stn_fwd_kernel(const FwdArgs a) {
-    extern __shared__ int4 s_tab[];  // [Wo] column entries, [Ho] row entries
-    const Geo& g = a.g;
-    const int C = g.C;
-    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-        Theta th;
-        th.load(a.theta + 6 * b);
-        const bool sep = th.separable();
-        float z = 1.0f;
-        bool active = true;
-        if (COMPOSITE) {
-            z = __ldg(a.z_pres + b);
-            active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
-        }
-        const float* __restrict__ Ub = a.U + (b / a.u_div) * (long long)g.S * C;
-        float* __restrict__ ob = a.out + b * (long long)g.N * C;
-        const float* __restrict__ cb = COMPOSITE ? a.canvas_in + b * (long long)g.N : nullptr;
-        const bool inplace = COMPOSITE && (a.canvas_in == a.out);
-
-        if (COMPOSITE && !active) {
-            // where(mask, ., 0): canvas + 0  (air_number_bbox_location.py:722-727)
-            if (!inplace)
-                for (int n = threadIdx.x; n < g.N; n += kThreads) ob[n] = __fadd_rn(cb[n], 0.0f);
-            continue;
-        }
-        if (sep) {
-            __syncthreads();  // previous image's readers are done with the tables
-            build_tables(s_tab, th, g);
-            __syncthreads();
-        }
-        for (int n = threadIdx.x; n < g.N; n += kThreads) {
-            int i, j;
-            split_n(g, n, i, j);
-            int x0, x1, r0, r1;
-            float ax, bx, ay, by;
-            if (sep) {
-                const int4 cx = s_tab[j], cy = s_tab[g.Wo + i];
-                x0 = cx.x; x1 = cx.y; ax = __int_as_float(cx.z); bx = __int_as_float(cx.w);
-                r0 = cy.x; r1 = cy.y; ay = __int_as_float(cy.z); by = __int_as_float(cy.w);
-            } else {
-                Axis X, Y;
-                taps_general(th, g, i, j, X, Y);
-                x0 = X.c0; x1 = X.c1; ax = X.a; bx = X.b;
-                r0 = Y.c0 * g.Ws; r1 = Y.c1 * g.Ws; ay = Y.a; by = Y.b;
-            }
-            if (r0 == r1) {
-                // y out of range: both row taps alias one row and the weights pair up as +w/-w in add_n
-                // order, so the reference's result is exactly +0 for finite inputs (DESIGN.md "borders").
-                if (COMPOSITE) {
-                    if (!inplace) ob[n] = __fadd_rn(cb[n], 0.0f);
-                } else {
-                    for (int c = 0; c < C; ++c) ob[(long long)n * C + c] = 0.0f;
-                }
-                continue;
-            }
-            // transformer.py:112-115
-            const float wa = __fmul_rn(ax, ay), wb = __fmul_rn(ax, by), wc = __fmul_rn(bx, ay), wd = __fmul_rn(bx, by);
-            const float* pa = Ub + (long long)(r0 + x0) * C;
-            const float* pb = Ub + (long long)(r1 + x0) * C;
-            const float* pc = Ub + (long long)(r0 + x1) * C;
-            const float* pd = Ub + (long long)(r1 + x1) * C;
-            for (int c = 0; c < C; ++c) {
-                // transformer.py:116  add_n in list order
-                float v = __fadd_rn(__fmul_rn(wa, __ldg(pa + c)), __fmul_rn(wb, __ldg(pb + c)));
-                v = __fadd_rn(v, __fmul_rn(wc, __ldg(pc + c)));
-                v = __fadd_rn(v, __fmul_rn(wd, __ldg(pd + c)));
-                if (COMPOSITE)
-                    ob[n] = __fadd_rn(cb[n], __fmul_rn(z, v));  // :724-726
-                else
-                    ob[(long long)n * C + c] = v;
-            }
-        }
-    }
-}
-
 // corner probe: same evaluation paths as the forward kernel (tables for separable thetas)
-__global__ void __launch_bounds__(kThreads) stn_corners_kernel(const float* theta, int32_t* corners, long long B,
+__global__ void __launch_bounds__(256) stn_corners_kernel(const float* theta, int32_t* corners, long long B,
                                                                 const Geo g) {
     extern __shared__ int4 s_tab[];
     const long long BN = B * (long long)g.N;
@@ -152,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) stn_corners_kernel(const float* thet
             build_tables(s_tab, th, g);
             __syncthreads();
         }
-        for (int n = threadIdx.x; n < g.N; n += kThreads) {
+        for (int n = threadIdx.x; n < g.N; n += 256) {
             int i, j;
             split_n(g, n, i, j);
             int x0, x1, y0, y1;
@@ -170,137 +74,6 @@ __global__ void __launch_bounds__(kThreads) stn_corners_kernel(const float* thet
             corners[2 * BN + o] = y0;
             corners[3 * BN + o] = y1;
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// backward, general path: scatter-add of dU (shared-memory accumulation tile when the source image
-// fits, L2 atomics otherwise) + dtheta by warp shuffles then a block reduction.
-// One CTA per SOURCE image (all u_div transforms of it), so dU needs no inter-CTA atomics and no
-// separate zero-fill pass: the CTA writes every element of dU[bs] exactly once (tile flush) or zero-fills
-// then REDs while the lines are still L2-resident.
-// ---------------------------------------------------------------------------------------------------
-struct BwdArgs {
-    const float* U;
-    const float* theta;
-    const float* gout;
-    float* dU;
-    float* dtheta;
-    // composite only
-    const float* z_pres;
-    const float* stop_sum;
-    float* dz;
-    float threshold;
-    long long Bsrc;
-    int u_div;
-    Geo g;
-};
-
-template <bool COMPOSITE, bool SMEM_ACC>
-__global__ void __launch_bounds__(kThreads) stn_bwd_kernel(const BwdArgs a) {
-    extern __shared__ int4 s_dyn[];
-    const Geo& g = a.g;
-    const int C = g.C;
-    int4* s_tab = s_dyn;                                                      // [Wo + Ho]
-    float* s_red = reinterpret_cast<float*>(s_dyn + g.Wo + g.Ho);             // [kWarps][8]
-    float* s_acc = s_red + kWarps * 8;                                        // [S*C] when SMEM_ACC
-    const int SC = g.S * C;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (long long bs = blockIdx.x; bs < a.Bsrc; bs += gridDim.x) {
-        const float* __restrict__ Ub = a.U + bs * (long long)SC;
-        float* __restrict__ dUb = a.dU ? a.dU + bs * (long long)SC : nullptr;
-        if (dUb) {
-            if (SMEM_ACC) {
-                for (int k = threadIdx.x; k < SC; k += kThreads) s_acc[k] = 0.0f;
-            } else {
-                for (int k = threadIdx.x; k < SC; k += kThreads) dUb[k] = 0.0f;
-            }
-        }
-        for (int t = 0; t < a.u_div; ++t) {
-            const long long b = bs * a.u_div + t;
-            Theta th;
-            th.load(a.theta + 6 * b);
-            const bool sep = th.separable();
-            float z = 1.0f;
-            bool active = true;
-            if (COMPOSITE) {
-                z = __ldg(a.z_pres + b);
-                active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
-            }
-            __syncthreads();  // tables/s_red free, zero-fill visible
-            if (sep && active) build_tables(s_tab, th, g);
-            __syncthreads();
-            float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (active) {
-                const float* __restrict__ gb = a.gout + b * (long long)g.N * C;
-                for (int n = threadIdx.x; n < g.N; n += kThreads) {
-                    int i, j;
-                    split_n(g, n, i, j);
-                    int x0, x1, r0, r1;
-                    float ax, bx, ay, by;
-                    if (sep) {
-                        const int4 cx = s_tab[j], cy = s_tab[g.Wo + i];
-                        x0 = cx.x; x1 = cx.y; ax = __int_as_float(cx.z); bx = __int_as_float(cx.w);
-                        r0 = cy.x; r1 = cy.y; ay = __int_as_float(cy.z); by = __int_as_float(cy.w);
-                    } else {
-                        Axis X, Y;
-                        taps_general(th, g, i, j, X, Y);
-                        x0 = X.c0; x1 = X.c1; ax = X.a; bx = X.b;
-                        r0 = Y.c0 * g.Ws; r1 = Y.c1 * g.Ws; ay = Y.a; by = Y.b;
-                    }
-                    // Out of range on an axis: the two taps alias one pixel with weights +w/-w, so every
-                    // gradient contribution cancels in exact arithmetic (DESIGN.md "borders").
-                    if (x0 == x1 || r0 == r1) continue;
-                    const int ia = (r0 + x0) * C, ib = (r1 + x0) * C, ic = (r0 + x1) * C, id = (r1 + x1) * C;
-                    const float wa = ax * ay, wb = ax * by, wc = bx * ay, wd = bx * by;
-                    float sx = 0.f, sy = 0.f;  // sum_c g*[ay(Ic-Ia)+by(Id-Ib)],  sum_c g*[ax(Ib-Ia)+bx(Id-Ic)]
-                    for (int c = 0; c < C; ++c) {
-                        const float gc = __ldg(gb + (long long)n * C + c);
-                        const float gv = COMPOSITE ? gc * z : gc;
-                        const float Ia = __ldg(Ub + ia + c), Ib = __ldg(Ub + ib + c);
-                        const float Ic = __ldg(Ub + ic + c), Id = __ldg(Ub + id + c);
-                        if (dUb) {
-                            float* acc = SMEM_ACC ? s_acc : dUb;
-                            atomicAdd(acc + ia + c, wa * gv);
-                            atomicAdd(acc + ib + c, wb * gv);
-                            atomicAdd(acc + ic + c, wc * gv);
-                            atomicAdd(acc + id + c, wd * gv);
-                        }
-                        sx += gv * (ay * (Ic - Ia) + by * (Id - Ib));
-                        sy += gv * (ax * (Ib - Ia) + bx * (Id - Ic));
-                        if (COMPOSITE) p[6] += gc * (wa * Ia + wb * Ib + wc * Ic + wd * Id);
-                    }
-                    const float dxs = sx * g.wsc * 0.5f, dys = sy * g.hsc * 0.5f;
-                    const float xt = lin_at(j, g.step_w), yt = lin_at(i, g.step_h);
-                    p[0] += dxs * xt; p[1] += dxs * yt; p[2] += dxs;
-                    p[3] += dys * xt; p[4] += dys * yt; p[5] += dys;
-                }
-            }
-            // dtheta / dz: warp shuffles, then a block reduction through shared memory
-#pragma unroll
-            for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 7; ++k) s_red[warp * 8 + k] = p[k];
-            }
-            __syncthreads();
-            if (threadIdx.x < 7) {
-                float v = 0.f;
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) v += s_red[w * 8 + threadIdx.x];
-                if (threadIdx.x < 6) {
-                    if (a.dtheta) a.dtheta[6 * b + threadIdx.x] = v;
-                } else if (COMPOSITE && a.dz) {
-                    a.dz[b] = v;
-                }
-            }
-        }
-        if (dUb && SMEM_ACC) {
-            __syncthreads();
-            for (int k = threadIdx.x; k < SC; k += kThreads) dUb[k] = s_acc[k];
-        }
-        __syncthreads();
     }
 }
 
@@ -341,32 +114,36 @@ static int set_smem(K kernel, size_t bytes) {
 template <bool COMPOSITE>
 static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     if (a.B == 0) return MOG_OK;
-    const size_t smem = (size_t)(a.g.Wo + a.g.Ho) * sizeof(int4);
-    if (int rc = set_smem(stn_fwd_kernel<COMPOSITE>, smem)) return rc;
-    stn_fwd_kernel<COMPOSITE><<<grid_for(a.B, 8), kThreads, smem, st>>>(a);
-    MOG_CUDA_LAUNCH_CHECK("stn_fwd_kernel");
+    const size_t smem = (size_t)kWarpsPerCta * a.g.Ho * sizeof(int4);
+    MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d too large for the per-warp row tables", a.g.Ho);
+    if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
+    const long long ctas = (a.B + kWarpsPerCta - 1) / kWarpsPerCta;
+    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, 8), kWarpThreads, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_fwd_warp_kernel");
+    return MOG_OK;
+}
+
+template <bool COMPOSITE, int NXC>
+static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)kWarpsPerCta * bwd_warp_smem_words(a.g) * sizeof(int);
+    MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d Ws=%d too large for the per-warp tables",
+                a.g.Ho, a.g.Wo, a.g.Ws);
+    if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC>, smem)) return rc;
+    const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
+    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, 8), kWarpThreads, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_warp_kernel");
     return MOG_OK;
 }
 
 template <bool COMPOSITE>
-static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
-    const size_t base = (size_t)(a.g.Wo + a.g.Ho) * sizeof(int4) + kWarps * 8 * sizeof(float);
-    const size_t tile = a.dU ? (size_t)a.g.S * a.g.C * sizeof(float) : 0;
-    const bool smem_acc = a.dU && base + tile <= (size_t)kMaxSmemBytes;
-    const size_t smem = base + (smem_acc ? tile : 0);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    const int grid = grid_for(a.Bsrc, per_sm);
-    if (smem_acc) {
-        if (int rc = set_smem(stn_bwd_kernel<COMPOSITE, true>, smem)) return rc;
-        stn_bwd_kernel<COMPOSITE, true><<<grid, kThreads, smem, st>>>(a);
-    } else {
-        if (int rc = set_smem(stn_bwd_kernel<COMPOSITE, false>, smem)) return rc;
-        stn_bwd_kernel<COMPOSITE, false><<<grid, kThreads, smem, st>>>(a);
-    }
-    MOG_CUDA_LAUNCH_CHECK("stn_bwd_kernel");
-    return MOG_OK;
+    const int nxc = (a.g.Ws + 31) / 32;
+    a.allow_sep = nxc <= 8 ? 1 : 0;  // wider sources use the general (atomic) path
+    if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);
+    if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st);
+    if (nxc <= 4) return launch_bwd_nxc<COMPOSITE, 4>(a, st);
+    return launch_bwd_nxc<COMPOSITE, 8>(a, st);
 }
 
 }  // namespace mog
@@ -407,7 +184,7 @@ extern "C" int mog_stn_corners(const float* theta, int32_t* corners, int64_t B, 
     const Geo g = make_geo(Hs, Ws, 1, Ho, Wo);
     const size_t smem = (size_t)(Wo + Ho) * sizeof(int4);
     if (int rc = set_smem(stn_corners_kernel, smem)) return rc;
-    stn_corners_kernel<<<grid_for(B, 8), kThreads, smem, (cudaStream_t)stream>>>(theta, corners, B, g);
+    stn_corners_kernel<<<grid_for(B, 8), 256, smem, (cudaStream_t)stream>>>(theta, corners, B, g);
     MOG_CUDA_LAUNCH_CHECK("stn_corners_kernel");
     return MOG_OK;
 }

@@ -1,0 +1,497 @@
+// Warp-per-image sampler kernels (sm_100a).
+//
+// The images of this workload are small (28x28 ... 256x256, one channel) and there are thousands of
+// them, so one WARP owns one image: no block barriers, 32-64 independent images in flight per SM to hide
+// the theta -> coordinates -> gather -> store latency chain, lanes run along the contiguous (x) axis so
+// every global access is a coalesced row segment.
+//
+// Separable thetas (t01 == t10 == 0: every AIR call site, air_number_bbox_location.py:513-531,565-584)
+// use per-row / per-column axis tables (bit-identical to the per-pixel evaluation, see Theta::separable).
+//   forward : per row one broadcast LDS.128 (row entry) + 4 gathers + 11 flops per pixel.
+//   backward: *gather form*, no atomics, deterministic.  With W_x[j][x] / W_y[i][y] the 1-D tap weights,
+//             dU = W_y^T (G W_x).  Rows are streamed in the order that makes y0 non-decreasing; for each
+//             output row the warp forms T[x] = sum_j W_x[j][x] g[i][j] from a per-warp shared-memory row
+//             buffer and folds it into two running source rows (y0, y0+1) held in registers; a source
+//             row is stored exactly once (coalesced) when the stream moves past it, untouched rows are
+//             zero-filled on the way.  dU is therefore written once and never read.
+// General affine thetas fall back, inside the same kernels, to per-pixel evaluation and (backward) to a
+// warp-local zero-fill followed by L2 atomics (red.global.add.f32) on the image's own dU lines.
+#pragma once
+#include "mog_common.cuh"
+
+namespace mog {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kWarpThreads = kWarpsPerCta * 32;
+
+struct FwdArgs {
+    const float* U;
+    const float* theta;
+    float* out;
+    // composite only
+    const float* z_pres;
+    const float* stop_sum;
+    const float* canvas_in;
+    float threshold;
+    long long B;
+    int u_div;
+    Geo g;
+};
+
+struct BwdArgs {
+    const float* U;
+    const float* theta;
+    const float* gout;
+    float* dU;
+    float* dtheta;
+    // composite only
+    const float* z_pres;
+    const float* stop_sum;
+    float* dz;
+    float threshold;
+    long long Bsrc;
+    int u_div;
+    int allow_sep;  // 0: source too wide for the streaming path's register rows -> general path only
+    Geo g;
+};
+
+// row-table entry: {y0*Ws, y1*Ws, ay, by}; column entry: {x0, x1, ax, bx}
+__device__ __forceinline__ int4 row_entry(const Theta& th, const Geo& g, int i) {
+    return pack_axis(axis_tap(affine_row(th.t[3], th.t[4], th.t[5], 0.0f, lin_at(i, g.step_h)), g.hsc, g.Hs), g.Ws);
+}
+__device__ __forceinline__ Axis col_axis(const Theta& th, const Geo& g, int j) {
+    return axis_tap(affine_row(th.t[0], th.t[1], th.t[2], lin_at(j, g.step_w), 0.0f), g.wsc, g.Ws);
+}
+
+// same with the row offsets in bytes (hot forward path: pointer + 32-bit byte offset = one IMAD.WIDE.U32)
+__device__ __forceinline__ int4 row_entry_bytes(const Theta& th, const Geo& g, int i) {
+    return pack_axis(axis_tap(affine_row(th.t[3], th.t[4], th.t[5], 0.0f, lin_at(i, g.step_h)), g.hsc, g.Hs),
+                     g.Ws * (int)sizeof(float));
+}
+
+// Hide a pointer's provenance from the optimiser so it stays a 64-bit base register instead of being
+// re-derived (4-6 integer instructions per tap) from the kernel argument inside the inner loop.
+template <typename T>
+__device__ __forceinline__ T* opaque(T* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
+__device__ __forceinline__ float ldg_f32(const char* p) { return __ldg(reinterpret_cast<const float*>(p)); }
+
+// zero p[begin, end) with 16-byte stores between the first and last 16-byte boundaries
+__device__ __forceinline__ void fill_zero(float* __restrict__ p, int begin, int end, int lane) {
+    if (end <= begin) return;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(p + begin) >> 2) & 3);  // floats past a 16-byte boundary
+    const int head = min(end, begin + ((4 - mis) & 3));
+    const int nv = (end - head) >> 2;
+    const int tail = head + 4 * nv;
+    if (begin + lane < head) p[begin + lane] = 0.0f;
+    float4* v = reinterpret_cast<float4*>(p + head);
+    for (int k = lane; k < nv; k += 32) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tail + lane < end) p[tail + lane] = 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward (also the fused write+composite forward)
+// ---------------------------------------------------------------------------------------------------
+template <bool COMPOSITE>
+__global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArgs a) {
+    extern __shared__ int4 s_dyn[];
+    const Geo& g = a.g;
+    const int C = g.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int4* s_row = s_dyn + warp * g.Ho;  // per-warp row table
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+
+    for (long long b = (long long)blockIdx.x * kWarpsPerCta + warp; b < a.B; b += nwarps) {
+        Theta th;
+        th.load(a.theta + 6 * b);
+        const bool sep = th.separable();
+        float z = 1.0f;
+        bool active = true;
+        if (COMPOSITE) {
+            z = __ldg(a.z_pres + b);
+            active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
+        }
+        const float* __restrict__ Ub = a.U + (b / a.u_div) * (long long)g.S * C;
+        float* __restrict__ ob = a.out + b * (long long)g.N * C;
+        const float* __restrict__ cb = COMPOSITE ? a.canvas_in + b * (long long)g.N : nullptr;
+        const bool inplace = COMPOSITE && (a.canvas_in == a.out);
+
+        if (COMPOSITE && !active) {
+            // where(mask, ., 0): canvas + 0  (air_number_bbox_location.py:722-727)
+            if (!inplace)
+                for (int n = lane; n < g.N; n += 32) ob[n] = __fadd_rn(cb[n], 0.0f);
+            continue;
+        }
+        if (sep && C == 1) {
+            // ---- hot path: axis-aligned theta, one channel ------------------------------------------
+            __syncwarp();  // previous image's readers are done with the row table
+            int ilo = g.Ho, ihi = -1;  // in-range rows form one interval (the coordinate map is monotone)
+            for (int i = lane; i < g.Ho; i += 32) {
+                const int4 e = row_entry_bytes(th, g, i);
+                s_row[i] = e;
+                if (e.x != e.y) { ilo = min(ilo, i); ihi = max(ihi, i); }
+            }
+            ilo = __reduce_min_sync(0xffffffffu, ilo);
+            ihi = __reduce_max_sync(0xffffffffu, ihi) + 1;
+            if (ihi <= ilo) { ilo = 0; ihi = 0; }
+            __syncwarp();
+            // y out of range: both row taps alias one row and the weights pair up as +w/-w in add_n order,
+            // so the reference's result is exactly +0 for finite inputs (DESIGN.md "borders"): those rows
+            // are zero-filled with wide stores; the in-place composite has nothing to add there.
+            if (!COMPOSITE) {
+                fill_zero(ob, 0, ilo * g.Wo, lane);
+                fill_zero(ob, ihi * g.Wo, g.N, lane);
+            } else if (!inplace) {
+                for (int n = lane; n < ilo * g.Wo; n += 32) ob[n] = __fadd_rn(cb[n], 0.0f);
+                for (int n = ihi * g.Wo + lane; n < g.N; n += 32) ob[n] = __fadd_rn(cb[n], 0.0f);
+            }
+            const int4* rows = s_row + ilo;
+            const int nrows = ihi - ilo;
+            for (int j0 = 0; j0 < g.Wo; j0 += 32) {
+                const int j = j0 + lane;
+                if (j >= g.Wo) continue;
+                const Axis X = col_axis(th, g, j);
+                const char* Ux0 = opaque(reinterpret_cast<const char*>(Ub + X.c0));
+                const char* Ux1 = opaque(reinterpret_cast<const char*>(Ub + X.c1));
+                float* orow = opaque(ob + (long long)ilo * g.Wo + j);
+                const float* crow = COMPOSITE ? opaque(cb + (long long)ilo * g.Wo + j) : nullptr;
+                // Rows in batches of RB: all 4*RB gathers are issued before the first dependent multiply /
+                // store, so one warp keeps 16 loads in flight (the stores would otherwise fence the loop).
+                constexpr int RB = 4;
+                int i = 0;
+                for (; i + RB <= nrows; i += RB) {
+                    int4 cy[RB];
+                    float I[RB][4], cin[RB];
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        cy[r] = rows[i + r];  // {y0*Ws*4, y1*Ws*4, ay, by}: byte offsets of the two source rows
+                        I[r][0] = ldg_f32(Ux0 + (unsigned)cy[r].x);
+                        I[r][1] = ldg_f32(Ux0 + (unsigned)cy[r].y);
+                        I[r][2] = ldg_f32(Ux1 + (unsigned)cy[r].x);
+                        I[r][3] = ldg_f32(Ux1 + (unsigned)cy[r].y);
+                        if (COMPOSITE) cin[r] = crow[r * g.Wo];
+                    }
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        const float ay = __int_as_float(cy[r].z), by = __int_as_float(cy[r].w);
+                        // transformer.py:112-116
+                        float v = __fadd_rn(__fmul_rn(__fmul_rn(X.a, ay), I[r][0]), __fmul_rn(__fmul_rn(X.a, by), I[r][1]));
+                        v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, ay), I[r][2]));
+                        v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, by), I[r][3]));
+                        if (COMPOSITE) v = __fadd_rn(cin[r], __fmul_rn(z, v));  // :724-726
+                        orow[r * g.Wo] = v;
+                    }
+                    orow += RB * g.Wo;
+                    if (COMPOSITE) crow += RB * g.Wo;
+                }
+                for (; i < nrows; ++i) {
+                    const int4 cy = rows[i];
+                    const float ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
+                    const float Ia = ldg_f32(Ux0 + (unsigned)cy.x), Ib = ldg_f32(Ux0 + (unsigned)cy.y);
+                    const float Ic = ldg_f32(Ux1 + (unsigned)cy.x), Id = ldg_f32(Ux1 + (unsigned)cy.y);
+                    float v = __fadd_rn(__fmul_rn(__fmul_rn(X.a, ay), Ia), __fmul_rn(__fmul_rn(X.a, by), Ib));
+                    v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, ay), Ic));
+                    v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, by), Id));
+                    if (COMPOSITE) {
+                        v = __fadd_rn(*crow, __fmul_rn(z, v));
+                        crow += g.Wo;
+                    }
+                    *orow = v;
+                    orow += g.Wo;
+                }
+            }
+            continue;
+        }
+        // ---- general affine theta and/or several channels: per-pixel evaluation -------------------------
+        for (int j0 = 0; j0 < g.Wo; j0 += 32) {
+            const int j = j0 + lane;
+            if (j >= g.Wo) continue;
+            for (int i = 0; i < g.Ho; ++i) {
+                Axis X, Y;
+                taps_general(th, g, i, j, X, Y);
+                const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
+                const long long n = (long long)i * g.Wo + j;
+                if (r0 == r1) {
+                    if (COMPOSITE) {
+                        if (!inplace) ob[n] = __fadd_rn(cb[n], 0.0f);
+                    } else {
+                        for (int c = 0; c < C; ++c) ob[n * C + c] = 0.0f;
+                    }
+                    continue;
+                }
+                // transformer.py:112-115
+                const float wa = __fmul_rn(X.a, Y.a), wb = __fmul_rn(X.a, Y.b), wc = __fmul_rn(X.b, Y.a), wd = __fmul_rn(X.b, Y.b);
+                const float* pa = Ub + (long long)(r0 + X.c0) * C;
+                const float* pb = Ub + (long long)(r1 + X.c0) * C;
+                const float* pc = Ub + (long long)(r0 + X.c1) * C;
+                const float* pd = Ub + (long long)(r1 + X.c1) * C;
+                for (int c = 0; c < C; ++c) {
+                    // transformer.py:116  add_n in list order
+                    float v = __fadd_rn(__fmul_rn(wa, __ldg(pa + c)), __fmul_rn(wb, __ldg(pb + c)));
+                    v = __fadd_rn(v, __fmul_rn(wc, __ldg(pc + c)));
+                    v = __fadd_rn(v, __fmul_rn(wd, __ldg(pd + c)));
+                    if (COMPOSITE)
+                        ob[n] = __fadd_rn(cb[n], __fmul_rn(z, v));  // :724-726
+                    else
+                        ob[n * C + c] = v;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward (also the fused write+composite backward)
+// ---------------------------------------------------------------------------------------------------
+// per-warp shared memory layout (in 4-byte words): row table 4*Ho | col table 4*Wo | run start Ws | run end Ws
+//                                                   | ga Wo | gb Wo
+__host__ __device__ inline int bwd_warp_smem_words(const Geo& g) { return 4 * g.Ho + 4 * g.Wo + 2 * g.Ws + 2 * g.Wo; }
+
+template <int NXC>
+struct RowAcc {
+    float a0[NXC], a1[NXC];
+};
+
+// store (first transform) or accumulate (later transforms of the same source image) one dU row
+template <int NXC>
+__device__ __forceinline__ void emit_row(float* __restrict__ dUb, int Ws, int y, const float (&acc)[NXC], int lane,
+                                         bool first) {
+#pragma unroll
+    for (int c = 0; c < NXC; ++c) {
+        const int x = c * 32 + lane;
+        if (x < Ws) {
+            float* p = dUb + (long long)y * Ws + x;
+            *p = first ? acc[c] : (*p + acc[c]);
+        }
+    }
+}
+
+__device__ __forceinline__ void zero_rows(float* __restrict__ dUb, int Ws, int y_begin, int y_end, int lane) {
+    const int n = (y_end - y_begin) * Ws;
+    float* p = dUb + (long long)y_begin * Ws;
+    for (int k = lane; k < n; k += 32) p[k] = 0.0f;
+}
+
+template <bool COMPOSITE, int NXC>
+__global__ void __launch_bounds__(kWarpThreads) stn_bwd_warp_kernel(const BwdArgs a) {
+    extern __shared__ int4 s_dyn[];
+    const Geo& g = a.g;
+    const int C = g.C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* s_base = reinterpret_cast<int*>(s_dyn) + warp * bwd_warp_smem_words(g);
+    int4* s_row = reinterpret_cast<int4*>(s_base);
+    int4* s_col = s_row + g.Ho;
+    int* s_start = reinterpret_cast<int*>(s_col + g.Wo);
+    int* s_end = s_start + g.Ws;
+    float* s_ga = reinterpret_cast<float*>(s_end + g.Ws);
+    float* s_gb = s_ga + g.Wo;
+    const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
+    const int SC = g.S * C;
+    const float half_wsc = g.wsc * 0.5f, half_hsc = g.hsc * 0.5f;
+
+    for (long long bs = (long long)blockIdx.x * kWarpsPerCta + warp; bs < a.Bsrc; bs += nwarps) {
+        const float* __restrict__ Ub = a.U + bs * (long long)SC;
+        float* __restrict__ dUb = a.dU ? a.dU + bs * (long long)SC : nullptr;
+        bool dU_started = false;  // has this source image's dU been fully written once already?
+
+        for (int t = 0; t < a.u_div; ++t) {
+            const long long b = bs * a.u_div + t;
+            Theta th;
+            th.load(a.theta + 6 * b);
+            const bool sep = th.separable() && C == 1 && a.allow_sep;
+            float z = 1.0f;
+            bool active = true;
+            if (COMPOSITE) {
+                z = __ldg(a.z_pres + b);
+                active = a.stop_sum ? (__ldg(a.stop_sum + b) < a.threshold) : true;
+            }
+            const float* __restrict__ gb = a.gout + b * (long long)g.N * C;
+            float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dtheta (6) + dz
+
+            if (!active) {
+                if (dUb && !dU_started) zero_rows(dUb, SC / g.Hs, 0, g.Hs, lane);
+            } else if (!sep) {
+                // ---------- general affine: warp-local zero fill, then L2 atomics on this image's lines ----
+                if (dUb && !dU_started) {
+                    for (int k = lane; k < SC; k += 32) dUb[k] = 0.0f;
+                    __syncwarp();
+                }
+                for (int j0 = 0; j0 < g.Wo; j0 += 32) {
+                    const int j = j0 + lane;
+                    if (j >= g.Wo) continue;
+                    const float xt = lin_at(j, g.step_w);
+                    for (int i = 0; i < g.Ho; ++i) {
+                        Axis X, Y;
+                        taps_general(th, g, i, j, X, Y);
+                        // Out of range on an axis: the two taps alias one pixel with weights +w/-w, so every
+                        // gradient contribution cancels in exact arithmetic (DESIGN.md "borders").
+                        if (X.c0 == X.c1 || Y.c0 == Y.c1) continue;
+                        const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
+                        const int ia = (r0 + X.c0) * C, ib = (r1 + X.c0) * C, ic = (r0 + X.c1) * C, id = (r1 + X.c1) * C;
+                        const float wa = X.a * Y.a, wb = X.a * Y.b, wc = X.b * Y.a, wd = X.b * Y.b;
+                        float sx = 0.f, sy = 0.f;
+                        const long long n = (long long)i * g.Wo + j;
+                        for (int c = 0; c < C; ++c) {
+                            const float gc = __ldg(gb + n * C + c);
+                            const float gv = COMPOSITE ? gc * z : gc;
+                            const float Ia = __ldg(Ub + ia + c), Ib = __ldg(Ub + ib + c);
+                            const float Ic = __ldg(Ub + ic + c), Id = __ldg(Ub + id + c);
+                            if (dUb) {
+                                atomicAdd(dUb + ia + c, wa * gv);
+                                atomicAdd(dUb + ib + c, wb * gv);
+                                atomicAdd(dUb + ic + c, wc * gv);
+                                atomicAdd(dUb + id + c, wd * gv);
+                            }
+                            sx += gv * (Y.a * (Ic - Ia) + Y.b * (Id - Ib));
+                            sy += gv * (X.a * (Ib - Ia) + X.b * (Id - Ic));
+                            if (COMPOSITE) p[6] += gc * (wa * Ia + wb * Ib + wc * Ic + wd * Id);
+                        }
+                        const float yt = lin_at(i, g.step_h);
+                        p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
+                        p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
+                    }
+                }
+                __syncwarp();
+            } else {
+                // ---------- separable: gather form, streaming over rows ----------------------------------
+                __syncwarp();
+                for (int i = lane; i < g.Ho; i += 32) s_row[i] = row_entry(th, g, i);
+                for (int j = lane; j < g.Wo; j += 32) s_col[j] = pack_axis(col_axis(th, g, j), 1);
+                for (int x = lane; x < g.Ws; x += 32) { s_start[x] = 0; s_end[x] = 0; }
+                __syncwarp();
+                // column runs: for source column x, [s_start[x], s_end[x]) = output columns whose x0 == x
+                // (contiguous: every rounding step of the coordinate map is monotone in j)
+                int jlo = g.Wo, jhi = -1;  // in-range output columns
+                for (int j = lane; j < g.Wo; j += 32) {
+                    const int4 cj = s_col[j];
+                    if (cj.x != cj.y) {
+                        jlo = min(jlo, j);
+                        jhi = max(jhi, j);
+                        bool first = true, last = true;
+                        if (j > 0) { const int4 q = s_col[j - 1]; first = !(q.x != q.y && q.x == cj.x); }
+                        if (j + 1 < g.Wo) { const int4 q = s_col[j + 1]; last = !(q.x != q.y && q.x == cj.x); }
+                        if (first) s_start[cj.x] = j;
+                        if (last) s_end[cj.x] = j + 1;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+                    jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+                }
+                __syncwarp();
+                const bool need_dU = dUb != nullptr;
+                const bool first_write = !dU_started;
+                float acc0[NXC], acc1[NXC];
+#pragma unroll
+                for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+                // per-lane run bounds for its source columns (x and x-1) in every x chunk
+                int ycur = -1;    // source row held in acc0 (acc1 holds ycur+1); -1 = nothing open
+                int yemit = 0;    // rows [0, yemit) of dU are final
+                const bool ascending = !(th.t[4] < 0.0f);
+                const int jc_lo = jhi >= 0 ? (jlo >> 5) : 0, jc_hi = jhi >= 0 ? (jhi >> 5) : -1;
+
+                for (int ii = 0; ii < g.Ho; ++ii) {
+                    const int i = ascending ? ii : g.Ho - 1 - ii;
+                    const int4 cy = s_row[i];
+                    if (cy.x == cy.y) continue;  // row out of range: contributions cancel
+                    const float ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
+                    const int r0 = cy.x, r1 = cy.y;
+                    if (need_dU) {
+                        const int y0 = r0 / g.Ws;
+                        if (y0 != ycur) {
+                            if (ycur >= 0) {
+                                emit_row<NXC>(dUb, g.Ws, ycur, acc0, lane, first_write);
+                                if (y0 == ycur + 1) {
+#pragma unroll
+                                    for (int c = 0; c < NXC; ++c) { acc0[c] = acc1[c]; acc1[c] = 0.f; }
+                                    yemit = ycur + 1;
+                                } else {
+                                    emit_row<NXC>(dUb, g.Ws, ycur + 1, acc1, lane, first_write);
+#pragma unroll
+                                    for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+                                    yemit = ycur + 2;
+                                }
+                            }
+                            if (first_write && y0 > yemit) zero_rows(dUb, g.Ws, yemit, y0, lane);
+                            yemit = max(yemit, y0);
+                            ycur = y0;
+                        }
+                    }
+                    const float yt = lin_at(i, g.step_h);
+                    const float* __restrict__ grow = gb + (long long)i * g.Wo;
+                    for (int jc = jc_lo; jc <= jc_hi; ++jc) {
+                        const int j = jc * 32 + lane;
+                        float ga = 0.f, gbv = 0.f;
+                        if (j < g.Wo) {
+                            const int4 cj = s_col[j];
+                            if (cj.x != cj.y) {
+                                const float ax = __int_as_float(cj.z), bx = __int_as_float(cj.w);
+                                const float gc = __ldg(grow + j);
+                                const float gv = COMPOSITE ? gc * z : gc;
+                                const float Ia = __ldg(Ub + r0 + cj.x), Ib = __ldg(Ub + r1 + cj.x);
+                                const float Ic = __ldg(Ub + r0 + cj.y), Id = __ldg(Ub + r1 + cj.y);
+                                const float sx = gv * (ay * (Ic - Ia) + by * (Id - Ib));
+                                const float sy = gv * (ax * (Ib - Ia) + bx * (Id - Ic));
+                                const float xt = lin_at(j, g.step_w);
+                                p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
+                                p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
+                                if (COMPOSITE)
+                                    p[6] += gc * ((ax * ay) * Ia + (ax * by) * Ib + (bx * ay) * Ic + (bx * by) * Id);
+                                ga = ax * gv;
+                                gbv = bx * gv;
+                            }
+                            if (need_dU) { s_ga[j] = ga; s_gb[j] = gbv; }
+                        }
+                    }
+                    if (need_dU) {
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < NXC; ++c) {
+                            const int x = c * 32 + lane;
+                            if (x < g.Ws) {
+                                float T = 0.f;
+                                for (int j = s_start[x], je = s_end[x]; j < je; ++j) T += s_ga[j];
+                                if (x > 0)
+                                    for (int j = s_start[x - 1], je = s_end[x - 1]; j < je; ++j) T += s_gb[j];
+                                acc0[c] += ay * T;
+                                acc1[c] += by * T;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (need_dU) {
+                    if (ycur >= 0) {
+                        emit_row<NXC>(dUb, g.Ws, ycur, acc0, lane, first_write);
+                        emit_row<NXC>(dUb, g.Ws, ycur + 1, acc1, lane, first_write);
+                        yemit = ycur + 2;
+                    }
+                    if (first_write && yemit < g.Hs) zero_rows(dUb, g.Ws, yemit, g.Hs, lane);
+                }
+                // scale: dx_s = dx*(Ws-1.001)/2, dy_s = dy*(Hs-1.001)/2   (transformer.py:75-76)
+                p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
+                p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
+            }
+            if (active && !sep) {
+                p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
+                p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
+            }
+            dU_started = true;
+            // dtheta / dz: warp shuffle reduction
+#pragma unroll
+            for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
+            if (lane == 0) {
+                if (a.dtheta) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) a.dtheta[6 * b + k] = p[k];
+                }
+                if (COMPOSITE && a.dz) a.dz[b] = p[6];
+            }
+        }
+    }
+}
+
+}  // namespace mog

@@ -65,4 +65,4 @@ def test_asr_c3_batch_256_seeded(cuda_device):
     close(per_image.detach().cpu().numpy(), ref["per_image"], VAL_RTOL, "per_image")
     close(t[1].grad.cpu().numpy(), ref["d_shifts"], GRAD_RTOL, "d_shifts")
     close(t[2].grad.cpu().numpy()[..., 0], ref["d_scales"], GRAD_RTOL, "d_scales")
-    assert float(margin) == 0.0 and torch.all(t[0].grad == 0)
+    assert float(margin.detach()) == 0.0 and torch.all(t[0].grad == 0)

@@ -168,7 +168,9 @@ def test_full_size_properties(cuda_device):
     o = M.transformer(Ug, tg, (28, 28))
     dU1, dt1 = torch.autograd.grad(o, (Ug, tg), go, retain_graph=True)
     dU2, dt2 = torch.autograd.grad(o, (Ug, tg), go * 2.0)
-    assert torch.allclose(dU2, dU1 * 2.0, rtol=1e-5, atol=1e-6) and torch.allclose(dt2, dt1 * 2.0, rtol=1e-4, atol=1e-4)
+    # (summation order may differ between launches: compare relative to the gradient scale)
+    assert float((dU2 - dU1 * 2.0).abs().max()) <= 1e-4 * float(dU1.abs().max())
+    assert float((dt2 - dt1 * 2.0).abs().max()) <= 1e-4 * float(dt1.abs().max())
     # sum(dU) == sum over in-range pixels of g (bilinear weights sum to 1): compare on the sample
     dUs, dts = R.transformer_backward(U[idx].cpu().numpy(), th[idx].cpu().numpy(), (28, 28), go[idx].cpu().numpy())
     aU, ath = R.backward_term_magnitudes(U[idx].cpu().numpy(), th[idx].cpu().numpy(), (28, 28), go[idx].cpu().numpy())
