@@ -245,37 +245,34 @@ __global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArg
 // ---------------------------------------------------------------------------------------------------
 // backward (also the fused write+composite backward)
 // ---------------------------------------------------------------------------------------------------
-// per-warp shared memory layout (in 4-byte words): row table 4*Ho | col table 4*Wo | run start Ws | run end Ws
-//                                                   | ga Wo | gb Wo
-__host__ __device__ inline int bwd_warp_smem_words(const Geo& g) { return 4 * g.Ho + 4 * g.Wo + 2 * g.Ws + 2 * g.Wo; }
+// per-warp shared memory layout (in 4-byte words): row table 4*Ho | col table 4*Wo | run table Ws | ga Wo | gb Wo
+// (rounded up to a multiple of 4 words so every warp's int4 tables stay 16-byte aligned)
+__host__ __device__ inline int bwd_warp_smem_words(const Geo& g) {
+    return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * g.Wo + 3) & ~3;
+}
 
 template <int NXC>
 struct RowAcc {
     float a0[NXC], a1[NXC];
 };
 
-// store (first transform) or accumulate (later transforms of the same source image) one dU row
+// store (first transform: the image was zero-filled up front) or accumulate (later transforms of the same
+// source image) the footprint columns [xlo, xlo + 32*nxc) of one dU row
 template <int NXC>
-__device__ __forceinline__ void emit_row(float* __restrict__ dUb, int Ws, int y, const float (&acc)[NXC], int lane,
-                                         bool first) {
+__device__ __forceinline__ void emit_row(float* __restrict__ dUb, int Ws, int y, int xlo, int nxc, const float (&acc)[NXC],
+                                         int lane, bool first) {
+    float* row = dUb + y * Ws + xlo + lane;
 #pragma unroll
     for (int c = 0; c < NXC; ++c) {
-        const int x = c * 32 + lane;
-        if (x < Ws) {
-            float* p = dUb + (long long)y * Ws + x;
+        if (c < nxc && xlo + c * 32 + lane < Ws) {
+            float* p = row + c * 32;
             *p = first ? acc[c] : (*p + acc[c]);
         }
     }
 }
 
-__device__ __forceinline__ void zero_rows(float* __restrict__ dUb, int Ws, int y_begin, int y_end, int lane) {
-    const int n = (y_end - y_begin) * Ws;
-    float* p = dUb + (long long)y_begin * Ws;
-    for (int k = lane; k < n; k += 32) p[k] = 0.0f;
-}
-
 template <bool COMPOSITE, int NXC>
-__global__ void __launch_bounds__(kWarpThreads) stn_bwd_warp_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const BwdArgs a) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
@@ -283,9 +280,8 @@ __global__ void __launch_bounds__(kWarpThreads) stn_bwd_warp_kernel(const BwdArg
     int* s_base = reinterpret_cast<int*>(s_dyn) + warp * bwd_warp_smem_words(g);
     int4* s_row = reinterpret_cast<int4*>(s_base);
     int4* s_col = s_row + g.Ho;
-    int* s_start = reinterpret_cast<int*>(s_col + g.Wo);
-    int* s_end = s_start + g.Ws;
-    float* s_ga = reinterpret_cast<float*>(s_end + g.Ws);
+    int* s_run = reinterpret_cast<int*>(s_col + g.Wo);
+    float* s_ga = reinterpret_cast<float*>(s_run + g.Ws);
     float* s_gb = s_ga + g.Wo;
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     const int SC = g.S * C;
@@ -311,7 +307,7 @@ __global__ void __launch_bounds__(kWarpThreads) stn_bwd_warp_kernel(const BwdArg
             float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dtheta (6) + dz
 
             if (!active) {
-                if (dUb && !dU_started) zero_rows(dUb, SC / g.Hs, 0, g.Hs, lane);
+                if (dUb && !dU_started) fill_zero(dUb, 0, SC, lane);
             } else if (!sep) {
                 // ---------- general affine: warp-local zero fill, then L2 atomics on this image's lines ----
                 if (dUb && !dU_started) {
@@ -356,120 +352,130 @@ __global__ void __launch_bounds__(kWarpThreads) stn_bwd_warp_kernel(const BwdArg
                 __syncwarp();
             } else {
                 // ---------- separable: gather form, streaming over rows ----------------------------------
-                __syncwarp();
-                for (int i = lane; i < g.Ho; i += 32) s_row[i] = row_entry(th, g, i);
-                for (int j = lane; j < g.Wo; j += 32) s_col[j] = pack_axis(col_axis(th, g, j), 1);
-                for (int x = lane; x < g.Ws; x += 32) { s_start[x] = 0; s_end[x] = 0; }
-                __syncwarp();
-                // column runs: for source column x, [s_start[x], s_end[x]) = output columns whose x0 == x
-                // (contiguous: every rounding step of the coordinate map is monotone in j)
-                int jlo = g.Wo, jhi = -1;  // in-range output columns
-                for (int j = lane; j < g.Wo; j += 32) {
-                    const int4 cj = s_col[j];
-                    if (cj.x != cj.y) {
-                        jlo = min(jlo, j);
-                        jhi = max(jhi, j);
-                        bool first = true, last = true;
-                        if (j > 0) { const int4 q = s_col[j - 1]; first = !(q.x != q.y && q.x == cj.x); }
-                        if (j + 1 < g.Wo) { const int4 q = s_col[j + 1]; last = !(q.x != q.y && q.x == cj.x); }
-                        if (first) s_start[cj.x] = j;
-                        if (last) s_end[cj.x] = j + 1;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
-                    jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
-                }
+                // Only in-range rows/columns contribute (out-of-range taps cancel, see above); both form one
+                // interval because every rounding step of the coordinate map is monotone.  For those,
+                // x1 = x0+1 and y1 = y0+1, so the table entries carry {c0, lin, a, b} and the four taps are
+                // base, base+1, base+Ws, base+Ws+1.
                 __syncwarp();
                 const bool need_dU = dUb != nullptr;
                 const bool first_write = !dU_started;
-                float acc0[NXC], acc1[NXC];
+                if (need_dU && first_write) fill_zero(dUb, 0, g.S, lane);  // footprint is overwritten below
+                int ilo = g.Ho, ihi = -1, jlo = g.Wo, jhi = -1;
+                for (int i = lane; i < g.Ho; i += 32) {
+                    const float yt = lin_at(i, g.step_h);
+                    const Axis Y = axis_tap(affine_row(th.t[3], th.t[4], th.t[5], 0.0f, yt), g.hsc, g.Hs);
+                    s_row[i] = make_int4(Y.c0, __float_as_int(yt), __float_as_int(Y.a), __float_as_int(Y.b));
+                    if (Y.c0 != Y.c1) { ilo = min(ilo, i); ihi = max(ihi, i); }
+                }
+                for (int j = lane; j < g.Wo; j += 32) {
+                    const float xt = lin_at(j, g.step_w);
+                    const Axis X = axis_tap(affine_row(th.t[0], th.t[1], th.t[2], xt, 0.0f), g.wsc, g.Ws);
+                    s_col[j] = make_int4(X.c0, __float_as_int(xt), __float_as_int(X.a), __float_as_int(X.b));
+                    if (X.c0 != X.c1) { jlo = min(jlo, j); jhi = max(jhi, j); }
+                }
+                for (int x = lane; x < g.Ws; x += 32) s_run[x] = 0;
+                ilo = __reduce_min_sync(0xffffffffu, ilo); ihi = __reduce_max_sync(0xffffffffu, ihi);
+                jlo = __reduce_min_sync(0xffffffffu, jlo); jhi = __reduce_max_sync(0xffffffffu, jhi);
+                __syncwarp();
+                if (ihi >= ilo && jhi >= jlo) {
+                    // column runs: source column x receives output columns [start, end) = {j : x0[j] == x},
+                    // packed start | end << 16 (empty = 0)
+                    int rmax = 0;
+                    for (int j = jlo + lane; j <= jhi; j += 32) {
+                        const int x0 = s_col[j].x;
+                        const bool first = (j == jlo) || (s_col[j - 1].x != x0);
+                        if (first) {
+                            int e = j + 1;
+                            while (e <= jhi && s_col[e].x == x0) ++e;
+                            s_run[x0] = j | (e << 16);
+                            rmax = max(rmax, e - j);
+                        }
+                    }
+                    rmax = __reduce_max_sync(0xffffffffu, rmax);
+                    const int xa = s_col[jlo].x, xb = s_col[jhi].x;
+                    const int xlo = min(xa, xb);                 // footprint columns [xlo, xhi + 1]
+                    const int fw = max(xa, xb) + 2 - xlo;
+                    const int nxc = (fw + 31) >> 5;              // <= NXC
+                    const int njc = (jhi - jlo + 32) >> 5;
+                    __syncwarp();
+                    int runA[NXC], runB[NXC];
 #pragma unroll
-                for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-                // per-lane run bounds for its source columns (x and x-1) in every x chunk
-                int ycur = -1;    // source row held in acc0 (acc1 holds ycur+1); -1 = nothing open
-                int yemit = 0;    // rows [0, yemit) of dU are final
-                const bool ascending = !(th.t[4] < 0.0f);
-                const int jc_lo = jhi >= 0 ? (jlo >> 5) : 0, jc_hi = jhi >= 0 ? (jhi >> 5) : -1;
-
-                for (int ii = 0; ii < g.Ho; ++ii) {
-                    const int i = ascending ? ii : g.Ho - 1 - ii;
-                    const int4 cy = s_row[i];
-                    if (cy.x == cy.y) continue;  // row out of range: contributions cancel
-                    const float ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
-                    const int r0 = cy.x, r1 = cy.y;
-                    if (need_dU) {
-                        const int y0 = r0 / g.Ws;
-                        if (y0 != ycur) {
+                    for (int c = 0; c < NXC; ++c) {
+                        const int x = xlo + c * 32 + lane;
+                        runA[c] = (c < nxc && x < g.Ws) ? s_run[x] : 0;
+                        runB[c] = (c < nxc && x - 1 < g.Ws && x > 0) ? s_run[x - 1] : 0;
+                    }
+                    float acc0[NXC], acc1[NXC];
+#pragma unroll
+                    for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+                    int ycur = -1;  // source row held in acc0 (acc1 holds ycur + 1); -1 = nothing open
+                    const bool ascending = !(th.t[4] < 0.0f);
+                    const int nrows = ihi - ilo + 1;
+                    for (int ii = 0; ii < nrows; ++ii) {
+                        const int i = ascending ? ilo + ii : ihi - ii;
+                        const int4 cy = s_row[i];
+                        const int y0 = cy.x;
+                        const float yt = __int_as_float(cy.y), ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
+                        if (need_dU && y0 != ycur) {
                             if (ycur >= 0) {
-                                emit_row<NXC>(dUb, g.Ws, ycur, acc0, lane, first_write);
+                                emit_row<NXC>(dUb, g.Ws, ycur, xlo, nxc, acc0, lane, first_write);
                                 if (y0 == ycur + 1) {
 #pragma unroll
                                     for (int c = 0; c < NXC; ++c) { acc0[c] = acc1[c]; acc1[c] = 0.f; }
-                                    yemit = ycur + 1;
                                 } else {
-                                    emit_row<NXC>(dUb, g.Ws, ycur + 1, acc1, lane, first_write);
+                                    emit_row<NXC>(dUb, g.Ws, ycur + 1, xlo, nxc, acc1, lane, first_write);
 #pragma unroll
                                     for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-                                    yemit = ycur + 2;
                                 }
                             }
-                            if (first_write && y0 > yemit) zero_rows(dUb, g.Ws, yemit, y0, lane);
-                            yemit = max(yemit, y0);
                             ycur = y0;
                         }
-                    }
-                    const float yt = lin_at(i, g.step_h);
-                    const float* __restrict__ grow = gb + (long long)i * g.Wo;
-                    for (int jc = jc_lo; jc <= jc_hi; ++jc) {
-                        const int j = jc * 32 + lane;
-                        float ga = 0.f, gbv = 0.f;
-                        if (j < g.Wo) {
-                            const int4 cj = s_col[j];
-                            if (cj.x != cj.y) {
-                                const float ax = __int_as_float(cj.z), bx = __int_as_float(cj.w);
+                        const float* __restrict__ grow = gb + i * g.Wo;
+                        const float* __restrict__ urow = Ub + y0 * g.Ws;
+                        for (int jc = 0; jc < njc; ++jc) {
+                            const int j = jlo + jc * 32 + lane;
+                            if (j <= jhi) {
+                                const int4 cj = s_col[j];
+                                const float xt = __int_as_float(cj.y), ax = __int_as_float(cj.z), bx = __int_as_float(cj.w);
                                 const float gc = __ldg(grow + j);
                                 const float gv = COMPOSITE ? gc * z : gc;
-                                const float Ia = __ldg(Ub + r0 + cj.x), Ib = __ldg(Ub + r1 + cj.x);
-                                const float Ic = __ldg(Ub + r0 + cj.y), Id = __ldg(Ub + r1 + cj.y);
+                                const float* pa = urow + cj.x;
+                                const float* pb = pa + g.Ws;
+                                const float Ia = __ldg(pa), Ic = __ldg(pa + 1), Ib = __ldg(pb), Id = __ldg(pb + 1);
                                 const float sx = gv * (ay * (Ic - Ia) + by * (Id - Ib));
                                 const float sy = gv * (ax * (Ib - Ia) + bx * (Id - Ic));
-                                const float xt = lin_at(j, g.step_w);
                                 p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
                                 p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
                                 if (COMPOSITE)
                                     p[6] += gc * ((ax * ay) * Ia + (ax * by) * Ib + (bx * ay) * Ic + (bx * by) * Id);
-                                ga = ax * gv;
-                                gbv = bx * gv;
+                                if (need_dU) { s_ga[j] = ax * gv; s_gb[j] = bx * gv; }
                             }
-                            if (need_dU) { s_ga[j] = ga; s_gb[j] = gbv; }
                         }
-                    }
-                    if (need_dU) {
-                        __syncwarp();
+                        if (need_dU) {
+                            __syncwarp();
 #pragma unroll
-                        for (int c = 0; c < NXC; ++c) {
-                            const int x = c * 32 + lane;
-                            if (x < g.Ws) {
-                                float T = 0.f;
-                                for (int j = s_start[x], je = s_end[x]; j < je; ++j) T += s_ga[j];
-                                if (x > 0)
-                                    for (int j = s_start[x - 1], je = s_end[x - 1]; j < je; ++j) T += s_gb[j];
-                                acc0[c] += ay * T;
-                                acc1[c] += by * T;
+                            for (int c = 0; c < NXC; ++c) {
+                                if (c < nxc) {
+                                    // T[x] = sum_{j in run(x)} ax[j] g[j] + sum_{j in run(x-1)} bx[j] g[j]; uniform
+                                    // trip count (rmax = longest run of this image), predicated per lane
+                                    const int a0 = runA[c] & 0xffff, a1 = runA[c] >> 16;
+                                    const int b0 = runB[c] & 0xffff, b1 = runB[c] >> 16;
+                                    float T = 0.f;
+                                    for (int r = 0; r < rmax; ++r) {
+                                        if (a0 + r < a1) T += s_ga[a0 + r];
+                                        if (b0 + r < b1) T += s_gb[b0 + r];
+                                    }
+                                    acc0[c] += ay * T;
+                                    acc1[c] += by * T;
+                                }
                             }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                }
-                if (need_dU) {
-                    if (ycur >= 0) {
-                        emit_row<NXC>(dUb, g.Ws, ycur, acc0, lane, first_write);
-                        emit_row<NXC>(dUb, g.Ws, ycur + 1, acc1, lane, first_write);
-                        yemit = ycur + 2;
+                    if (need_dU && ycur >= 0) {
+                        emit_row<NXC>(dUb, g.Ws, ycur, xlo, nxc, acc0, lane, first_write);
+                        emit_row<NXC>(dUb, g.Ws, ycur + 1, xlo, nxc, acc1, lane, first_write);
                     }
-                    if (first_write && yemit < g.Hs) zero_rows(dUb, g.Ws, yemit, g.Hs, lane);
                 }
                 // scale: dx_s = dx*(Ws-1.001)/2, dy_s = dy*(Hs-1.001)/2   (transformer.py:75-76)
                 p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
