@@ -245,10 +245,11 @@ __global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArg
 // ---------------------------------------------------------------------------------------------------
 // backward (also the fused write+composite backward)
 // ---------------------------------------------------------------------------------------------------
-// per-warp shared memory layout (in 4-byte words): row table 4*Ho | col table 4*Wo | run table Ws | ga Wo | gb Wo
+// per-warp shared memory layout (in 4-byte words): row table 4*Ho | col table 4*Wo | run table Ws |
+// ga [kBwdRB][Wo+1] | gb [kBwdRB][Wo+1]   (column Wo of every ga/gb row is a zero slot)
 // (rounded up to a multiple of 4 words so every warp's int4 tables stay 16-byte aligned)
 __host__ __device__ inline int bwd_warp_smem_words(const Geo& g) {
-    return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * g.Wo + 3) & ~3;
+    return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * 4 * (g.Wo + 1) + 3) & ~3;  // 4 = kBwdRB
 }
 
 template <int NXC>
@@ -257,22 +258,18 @@ struct RowAcc {
 };
 
 // store (first transform: the image was zero-filled up front) or accumulate (later transforms of the same
-// source image) the footprint columns [xlo, xlo + 32*nxc) of one dU row
-template <int NXC>
-__device__ __forceinline__ void emit_row(float* __restrict__ dUb, int Ws, int y, int xlo, int nxc, const float (&acc)[NXC],
-                                         int lane, bool first) {
-    float* row = dUb + y * Ws + xlo + lane;
-#pragma unroll
-    for (int c = 0; c < NXC; ++c) {
-        if (c < nxc && xlo + c * 32 + lane < Ws) {
-            float* p = row + c * 32;
-            *p = first ? acc[c] : (*p + acc[c]);
-        }
+// source image) one dU element
+__device__ __forceinline__ void emit_px(char* p, float v, bool ok, bool first) {
+    if (ok) {
+        float* q = reinterpret_cast<float*>(p);
+        *q = first ? v : (*q + v);
     }
 }
 
+constexpr int kBwdRB = 4;  // rows per batch of the streaming backward
+
 template <bool COMPOSITE, int NXC>
-__global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kWarpThreads, 2) stn_bwd_warp_kernel(const BwdArgs a) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
@@ -282,7 +279,12 @@ __global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const Bwd
     int4* s_col = s_row + g.Ho;
     int* s_run = reinterpret_cast<int*>(s_col + g.Wo);
     float* s_ga = reinterpret_cast<float*>(s_run + g.Ws);
-    float* s_gb = s_ga + g.Wo;
+    float* s_gb = s_ga + kBwdRB * (g.Wo + 1);
+    if (lane < kBwdRB) {  // zero slots read by empty run positions
+        s_ga[lane * (g.Wo + 1) + g.Wo] = 0.0f;
+        s_gb[lane * (g.Wo + 1) + g.Wo] = 0.0f;
+    }
+    __syncwarp();
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     const int SC = g.S * C;
     const float half_wsc = g.wsc * 0.5f, half_hsc = g.hsc * 0.5f;
@@ -354,23 +356,24 @@ __global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const Bwd
                 // ---------- separable: gather form, streaming over rows ----------------------------------
                 // Only in-range rows/columns contribute (out-of-range taps cancel, see above); both form one
                 // interval because every rounding step of the coordinate map is monotone.  For those,
-                // x1 = x0+1 and y1 = y0+1, so the table entries carry {c0, lin, a, b} and the four taps are
-                // base, base+1, base+Ws, base+Ws+1.
+                // x1 = x0+1 and y1 = y0+1: table entries are {byte offset of c0, lin, a, b} and the four taps
+                // sit at base, base+4, base+Ws*4, base+Ws*4+4.
                 __syncwarp();
                 const bool need_dU = dUb != nullptr;
                 const bool first_write = !dU_started;
                 if (need_dU && first_write) fill_zero(dUb, 0, g.S, lane);  // footprint is overwritten below
+                const int ws4 = g.Ws * 4;
                 int ilo = g.Ho, ihi = -1, jlo = g.Wo, jhi = -1;
                 for (int i = lane; i < g.Ho; i += 32) {
                     const float yt = lin_at(i, g.step_h);
                     const Axis Y = axis_tap(affine_row(th.t[3], th.t[4], th.t[5], 0.0f, yt), g.hsc, g.Hs);
-                    s_row[i] = make_int4(Y.c0, __float_as_int(yt), __float_as_int(Y.a), __float_as_int(Y.b));
+                    s_row[i] = make_int4(Y.c0 * ws4, __float_as_int(yt), __float_as_int(Y.a), __float_as_int(Y.b));
                     if (Y.c0 != Y.c1) { ilo = min(ilo, i); ihi = max(ihi, i); }
                 }
                 for (int j = lane; j < g.Wo; j += 32) {
                     const float xt = lin_at(j, g.step_w);
                     const Axis X = axis_tap(affine_row(th.t[0], th.t[1], th.t[2], xt, 0.0f), g.wsc, g.Ws);
-                    s_col[j] = make_int4(X.c0, __float_as_int(xt), __float_as_int(X.a), __float_as_int(X.b));
+                    s_col[j] = make_int4(X.c0 * 4, __float_as_int(xt), __float_as_int(X.a), __float_as_int(X.b));
                     if (X.c0 != X.c1) { jlo = min(jlo, j); jhi = max(jhi, j); }
                 }
                 for (int x = lane; x < g.Ws; x += 32) s_run[x] = 0;
@@ -387,12 +390,12 @@ __global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const Bwd
                         if (first) {
                             int e = j + 1;
                             while (e <= jhi && s_col[e].x == x0) ++e;
-                            s_run[x0] = j | (e << 16);
+                            s_run[x0 >> 2] = j | (e << 16);
                             rmax = max(rmax, e - j);
                         }
                     }
                     rmax = __reduce_max_sync(0xffffffffu, rmax);
-                    const int xa = s_col[jlo].x, xb = s_col[jhi].x;
+                    const int xa = s_col[jlo].x >> 2, xb = s_col[jhi].x >> 2;
                     const int xlo = min(xa, xb);                 // footprint columns [xlo, xhi + 1]
                     const int fw = max(xa, xb) + 2 - xlo;
                     const int nxc = (fw + 31) >> 5;              // <= NXC
@@ -408,73 +411,113 @@ __global__ void __launch_bounds__(kWarpThreads, 3) stn_bwd_warp_kernel(const Bwd
                     float acc0[NXC], acc1[NXC];
 #pragma unroll
                     for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-                    int ycur = -1;  // source row held in acc0 (acc1 holds ycur + 1); -1 = nothing open
+                    int offcur = -1;  // byte offset of the source row held in acc0 (acc1: next row); -1 = none
                     const bool ascending = !(th.t[4] < 0.0f);
                     const int nrows = ihi - ilo + 1;
-                    for (int ii = 0; ii < nrows; ++ii) {
-                        const int i = ascending ? ilo + ii : ihi - ii;
-                        const int4 cy = s_row[i];
-                        const int y0 = cy.x;
-                        const float yt = __int_as_float(cy.y), ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
-                        if (need_dU && y0 != ycur) {
-                            if (ycur >= 0) {
-                                emit_row<NXC>(dUb, g.Ws, ycur, xlo, nxc, acc0, lane, first_write);
-                                if (y0 == ycur + 1) {
-#pragma unroll
-                                    for (int c = 0; c < NXC; ++c) { acc0[c] = acc1[c]; acc1[c] = 0.f; }
-                                } else {
-                                    emit_row<NXC>(dUb, g.Ws, ycur + 1, xlo, nxc, acc1, lane, first_write);
-#pragma unroll
-                                    for (int c = 0; c < NXC; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
-                                }
-                            }
-                            ycur = y0;
-                        }
-                        const float* __restrict__ grow = gb + i * g.Wo;
-                        const float* __restrict__ urow = Ub + y0 * g.Ws;
+                    const char* Ubc = opaque(reinterpret_cast<const char*>(Ub));
+                    char* dUbc = reinterpret_cast<char*>(dUb) + (xlo + lane) * 4;
+                    const int P = g.Wo + 1;  // pitch of the per-row ga/gb buffers; column Wo is a zero slot
+
+                    for (int ii0 = 0; ii0 < nrows; ii0 += kBwdRB) {
+                        const int nb = min(kBwdRB, nrows - ii0);
+                        // ---- phase 1 (output-column side): loads of kBwdRB rows in flight together ----
                         for (int jc = 0; jc < njc; ++jc) {
                             const int j = jlo + jc * 32 + lane;
-                            if (j <= jhi) {
-                                const int4 cj = s_col[j];
-                                const float xt = __int_as_float(cj.y), ax = __int_as_float(cj.z), bx = __int_as_float(cj.w);
-                                const float gc = __ldg(grow + j);
-                                const float gv = COMPOSITE ? gc * z : gc;
-                                const float* pa = urow + cj.x;
-                                const float* pb = pa + g.Ws;
-                                const float Ia = __ldg(pa), Ic = __ldg(pa + 1), Ib = __ldg(pb), Id = __ldg(pb + 1);
-                                const float sx = gv * (ay * (Ic - Ia) + by * (Id - Ib));
-                                const float sy = gv * (ax * (Ib - Ia) + bx * (Id - Ic));
-                                p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
-                                p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
-                                if (COMPOSITE)
-                                    p[6] += gc * ((ax * ay) * Ia + (ax * by) * Ib + (bx * ay) * Ic + (bx * by) * Id);
-                                if (need_dU) { s_ga[j] = ax * gv; s_gb[j] = bx * gv; }
-                            }
-                        }
-                        if (need_dU) {
-                            __syncwarp();
+                            if (j > jhi) continue;
+                            const int4 cj = s_col[j];
+                            const float xt = __int_as_float(cj.y), ax = __int_as_float(cj.z), bx = __int_as_float(cj.w);
+                            int4 cy[kBwdRB];
+                            float gq[kBwdRB], I[kBwdRB][4];
 #pragma unroll
-                            for (int c = 0; c < NXC; ++c) {
-                                if (c < nxc) {
-                                    // T[x] = sum_{j in run(x)} ax[j] g[j] + sum_{j in run(x-1)} bx[j] g[j]; uniform
-                                    // trip count (rmax = longest run of this image), predicated per lane
-                                    const int a0 = runA[c] & 0xffff, a1 = runA[c] >> 16;
-                                    const int b0 = runB[c] & 0xffff, b1 = runB[c] >> 16;
-                                    float T = 0.f;
-                                    for (int r = 0; r < rmax; ++r) {
-                                        if (a0 + r < a1) T += s_ga[a0 + r];
-                                        if (b0 + r < b1) T += s_gb[b0 + r];
-                                    }
-                                    acc0[c] += ay * T;
-                                    acc1[c] += by * T;
+                            for (int r = 0; r < kBwdRB; ++r) {
+                                if (r < nb) {
+                                    const int i = ascending ? ilo + ii0 + r : ihi - ii0 - r;
+                                    cy[r] = s_row[i];
+                                    gq[r] = __ldg(gb + i * g.Wo + j);
+                                    const char* pa = Ubc + (unsigned)(cy[r].x + cj.x);
+                                    const char* pb = pa + ws4;
+                                    I[r][0] = ldg_f32(pa); I[r][2] = ldg_f32(pa + 4);
+                                    I[r][1] = ldg_f32(pb); I[r][3] = ldg_f32(pb + 4);
                                 }
                             }
-                            __syncwarp();
+#pragma unroll
+                            for (int r = 0; r < kBwdRB; ++r) {
+                                if (r < nb) {
+                                    const float yt = __int_as_float(cy[r].y), ay = __int_as_float(cy[r].z), by = __int_as_float(cy[r].w);
+                                    const float gv = COMPOSITE ? gq[r] * z : gq[r];
+                                    const float sx = gv * (ay * (I[r][2] - I[r][0]) + by * (I[r][3] - I[r][1]));
+                                    const float sy = gv * (ax * (I[r][1] - I[r][0]) + bx * (I[r][3] - I[r][2]));
+                                    p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
+                                    p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
+                                    if (COMPOSITE)
+                                        p[6] += gq[r] * ((ax * ay) * I[r][0] + (ax * by) * I[r][1] + (bx * ay) * I[r][2] + (bx * by) * I[r][3]);
+                                    if (need_dU) { s_ga[r * P + j] = ax * gv; s_gb[r * P + j] = bx * gv; }
+                                }
+                            }
                         }
+                        if (!need_dU) continue;
+                        __syncwarp();
+                        // ---- phase 2 (source-column side): T[x] = sum_{j in run(x)} ax g + sum_{j in run(x-1)} bx g
+                        //      uniform trip count rmax (longest run of this image); empty slots read a zero.
+                        //      Each 32-column chunk then walks the batch's rows with its own copy of the
+                        //      stream state: a source row is stored once, when the stream moves past it. ----
+                        int off_end = offcur;
+#pragma unroll
+                        for (int c = 0; c < NXC; ++c) {
+                            if (c < nxc) {
+                                const int a0 = runA[c] & 0xffff, a1 = runA[c] >> 16;
+                                const int b0 = runB[c] & 0xffff, b1 = runB[c] >> 16;
+                                float T[kBwdRB];
+#pragma unroll
+                                for (int r = 0; r < kBwdRB; ++r) T[r] = 0.f;
+                                for (int q = 0; q < rmax; ++q) {
+                                    const int ia = (a0 + q < a1) ? a0 + q : g.Wo;
+                                    const int ib = (b0 + q < b1) ? b0 + q : g.Wo;
+#pragma unroll
+                                    for (int r = 0; r < kBwdRB; ++r) T[r] += s_ga[r * P + ia] + s_gb[r * P + ib];
+                                }
+                                const bool xok = xlo + c * 32 + lane < g.Ws;
+                                char* colp = dUbc + c * 128;
+                                int oc = offcur;
+                                float v0 = acc0[c], v1 = acc1[c];
+#pragma unroll
+                                for (int r = 0; r < kBwdRB; ++r) {
+                                    if (r < nb) {
+                                        const int i = ascending ? ilo + ii0 + r : ihi - ii0 - r;
+                                        const int4 cy = s_row[i];
+                                        const int off = cy.x;
+                                        if (off != oc) {
+                                            if (oc >= 0) {
+                                                emit_px(colp + oc, v0, xok, first_write);
+                                                if (off == oc + ws4) {
+                                                    v0 = v1; v1 = 0.f;
+                                                } else {
+                                                    emit_px(colp + oc + ws4, v1, xok, first_write);
+                                                    v0 = 0.f; v1 = 0.f;
+                                                }
+                                            }
+                                            oc = off;
+                                        }
+                                        v0 += __int_as_float(cy.z) * T[r];
+                                        v1 += __int_as_float(cy.w) * T[r];
+                                    }
+                                }
+                                acc0[c] = v0; acc1[c] = v1;
+                                off_end = oc;
+                            }
+                        }
+                        offcur = off_end;
+                        __syncwarp();
                     }
-                    if (need_dU && ycur >= 0) {
-                        emit_row<NXC>(dUb, g.Ws, ycur, xlo, nxc, acc0, lane, first_write);
-                        emit_row<NXC>(dUb, g.Ws, ycur + 1, xlo, nxc, acc1, lane, first_write);
+                    if (need_dU && offcur >= 0) {
+#pragma unroll
+                        for (int c = 0; c < NXC; ++c) {
+                            if (c < nxc) {
+                                const bool xok = xlo + c * 32 + lane < g.Ws;
+                                emit_px(dUbc + c * 128 + offcur, acc0[c], xok, first_write);
+                                emit_px(dUbc + c * 128 + offcur + ws4, acc1[c], xok, first_write);
+                            }
+                        }
                     }
                 }
                 // scale: dx_s = dx*(Ws-1.001)/2, dy_s = dy*(Hs-1.001)/2   (transformer.py:75-76)
