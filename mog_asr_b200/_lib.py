@@ -7,7 +7,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libmogstn.so")
+SO_PATH = os.environ.get("MOG_SO") or os.path.join(_PKG, "libmogstn.so")  # MOG_SO: tuning experiments only
 
 MOG_ASR_MAX_STEPS = 16
 MOG_ASR_MAX_COUNTS = 8

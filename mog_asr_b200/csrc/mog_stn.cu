@@ -118,7 +118,7 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d too large for the per-warp row tables", a.g.Ho);
     if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
     const long long ctas = (a.B + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, 8), kWarpThreads, smem, st>>>(a);
+    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, 64 / kWarpsPerCta), kWarpThreads, smem, st>>>(a);
     MOG_CUDA_LAUNCH_CHECK("stn_fwd_warp_kernel");
     return MOG_OK;
 }
@@ -130,7 +130,7 @@ static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
                 a.g.Ho, a.g.Wo, a.g.Ws);
     if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC>, smem)) return rc;
     const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, 8), kWarpThreads, smem, st>>>(a);
+    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, 64 / kWarpsPerCta), kWarpThreads, smem, st>>>(a);
     MOG_CUDA_LAUNCH_CHECK("stn_bwd_warp_kernel");
     return MOG_OK;
 }

@@ -21,7 +21,27 @@
 
 namespace mog {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef MOG_BWD_RB
+#define MOG_BWD_RB 4
+#endif
+#ifndef MOG_FWD_PREFETCH
+#define MOG_FWD_PREFETCH 0
+#endif
+#ifndef MOG_FWD_RB
+#define MOG_FWD_RB 8
+#endif
+#ifndef MOG_BWD_MINB
+#define MOG_BWD_MINB 10
+#endif
+#ifndef MOG_FWD_MINB
+#define MOG_FWD_MINB 16
+#endif
+constexpr int kBwdRB = MOG_BWD_RB;  // rows per batch of the streaming backward
+constexpr int kFwdRB = MOG_FWD_RB;  // rows per batch of the forward hot loop
+#ifndef MOG_WARPS_PER_CTA
+#define MOG_WARPS_PER_CTA 2
+#endif
+constexpr int kWarpsPerCta = MOG_WARPS_PER_CTA;
 constexpr int kWarpThreads = kWarpsPerCta * 32;
 
 struct FwdArgs {
@@ -91,11 +111,61 @@ __device__ __forceinline__ void fill_zero(float* __restrict__ p, int begin, int 
     if (tail + lane < end) p[tail + lane] = 0.0f;
 }
 
+// General affine theta and/or several channels: per-pixel evaluation of transformer.py:75-116.  Kept out of
+// line so that its register needs do not constrain the hot (separable, one channel) path.
+// (scalar arguments only: taking the address of the kernel-parameter struct would force a local copy)
+template <bool COMPOSITE>
+__device__ __noinline__ void fwd_general_image(const float* __restrict__ Ub, float* __restrict__ ob,
+                                               const float* __restrict__ cb, float t0, float t1, float t2, float t3,
+                                               float t4, float t5, float z, bool inplace, int lane, int Hs, int Ws,
+                                               int C, int Ho, int Wo, float step_w, float step_h, float wsc, float hsc) {
+    Theta th;
+    th.t[0] = t0; th.t[1] = t1; th.t[2] = t2; th.t[3] = t3; th.t[4] = t4; th.t[5] = t5;
+    Geo g;
+    g.Hs = Hs; g.Ws = Ws; g.C = C; g.Ho = Ho; g.Wo = Wo; g.N = Ho * Wo; g.S = Hs * Ws;
+    g.step_w = step_w; g.step_h = step_h; g.wsc = wsc; g.hsc = hsc; g.magic_wo = 0;
+    for (int j0 = 0; j0 < g.Wo; j0 += 32) {
+        const int j = j0 + lane;
+        if (j >= g.Wo) continue;
+        for (int i = 0; i < g.Ho; ++i) {
+            Axis X, Y;
+            taps_general(th, g, i, j, X, Y);
+            const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
+            const long long n = (long long)i * g.Wo + j;
+            if (r0 == r1) {
+                // y out of range: exactly +0 in the reference (DESIGN.md "borders")
+                if (COMPOSITE) {
+                    if (!inplace) ob[n] = __fadd_rn(cb[n], 0.0f);
+                } else {
+                    for (int c = 0; c < C; ++c) ob[n * C + c] = 0.0f;
+                }
+                continue;
+            }
+            // transformer.py:112-115
+            const float wa = __fmul_rn(X.a, Y.a), wb = __fmul_rn(X.a, Y.b), wc = __fmul_rn(X.b, Y.a), wd = __fmul_rn(X.b, Y.b);
+            const float* pa = Ub + (long long)(r0 + X.c0) * C;
+            const float* pb = Ub + (long long)(r1 + X.c0) * C;
+            const float* pc = Ub + (long long)(r0 + X.c1) * C;
+            const float* pd = Ub + (long long)(r1 + X.c1) * C;
+            for (int c = 0; c < C; ++c) {
+                // transformer.py:116  add_n in list order
+                float v = __fadd_rn(__fmul_rn(wa, __ldg(pa + c)), __fmul_rn(wb, __ldg(pb + c)));
+                v = __fadd_rn(v, __fmul_rn(wc, __ldg(pc + c)));
+                v = __fadd_rn(v, __fmul_rn(wd, __ldg(pd + c)));
+                if (COMPOSITE)
+                    ob[n] = __fadd_rn(cb[n], __fmul_rn(z, v));  // :724-726
+                else
+                    ob[n * C + c] = v;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward (also the fused write+composite forward)
 // ---------------------------------------------------------------------------------------------------
 template <bool COMPOSITE>
-__global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kernel(const FwdArgs a) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
@@ -103,9 +173,19 @@ __global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArg
     int4* s_row = s_dyn + warp * g.Ho;  // per-warp row table
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
 
-    for (long long b = (long long)blockIdx.x * kWarpsPerCta + warp; b < a.B; b += nwarps) {
+    const long long b_first = (long long)blockIdx.x * kWarpsPerCta + warp;
+#if MOG_FWD_PREFETCH
+    Theta th_next;
+    if (b_first < a.B) th_next.load(a.theta + 6 * b_first);
+#endif
+    for (long long b = b_first; b < a.B; b += nwarps) {
+#if MOG_FWD_PREFETCH
+        const Theta th = th_next;
+        if (b + nwarps < a.B) th_next.load(a.theta + 6 * (b + nwarps));  // prefetch: hides one DRAM latency per image
+#else
         Theta th;
         th.load(a.theta + 6 * b);
+#endif
         const bool sep = th.separable();
         float z = 1.0f;
         bool active = true;
@@ -157,88 +237,46 @@ __global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArg
                 const char* Ux1 = opaque(reinterpret_cast<const char*>(Ub + X.c1));
                 float* orow = opaque(ob + (long long)ilo * g.Wo + j);
                 const float* crow = COMPOSITE ? opaque(cb + (long long)ilo * g.Wo + j) : nullptr;
-                // Rows in batches of RB: all 4*RB gathers are issued before the first dependent multiply /
-                // store, so one warp keeps 16 loads in flight (the stores would otherwise fence the loop).
-                constexpr int RB = 4;
-                int i = 0;
-                for (; i + RB <= nrows; i += RB) {
-                    int4 cy[RB];
-                    float I[RB][4], cin[RB];
+                // Rows in batches of kFwdRB: all 4*kFwdRB gathers are issued before the first dependent
+                // multiply / store, so one warp keeps 32 loads in flight (the stores would otherwise fence
+                // the loop); the tail batch is predicated rather than serialised.
+                for (int i0 = 0; i0 < nrows; i0 += kFwdRB) {
+                    const int nb = nrows - i0;
+                    float I[kFwdRB][4], cin[kFwdRB];
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        cy[r] = rows[i + r];  // {y0*Ws*4, y1*Ws*4, ay, by}: byte offsets of the two source rows
-                        I[r][0] = ldg_f32(Ux0 + (unsigned)cy[r].x);
-                        I[r][1] = ldg_f32(Ux0 + (unsigned)cy[r].y);
-                        I[r][2] = ldg_f32(Ux1 + (unsigned)cy[r].x);
-                        I[r][3] = ldg_f32(Ux1 + (unsigned)cy[r].y);
-                        if (COMPOSITE) cin[r] = crow[r * g.Wo];
+                    for (int r = 0; r < kFwdRB; ++r) {
+                        // tail rows re-load the batch's last valid row (always a legal address) instead of
+                        // predicating the loads; only their stores are skipped
+                        const int rr = min(r, nb - 1);
+                        const int4 cy = rows[i0 + rr];  // {y0*Ws*4, y1*Ws*4, ay, by}: byte offsets of the source rows
+                        I[r][0] = ldg_f32(Ux0 + (unsigned)cy.x);
+                        I[r][1] = ldg_f32(Ux0 + (unsigned)cy.y);
+                        I[r][2] = ldg_f32(Ux1 + (unsigned)cy.x);
+                        I[r][3] = ldg_f32(Ux1 + (unsigned)cy.y);
+                        if (COMPOSITE) cin[r] = crow[rr * g.Wo];
                     }
 #pragma unroll
-                    for (int r = 0; r < RB; ++r) {
-                        const float ay = __int_as_float(cy[r].z), by = __int_as_float(cy[r].w);
-                        // transformer.py:112-116
-                        float v = __fadd_rn(__fmul_rn(__fmul_rn(X.a, ay), I[r][0]), __fmul_rn(__fmul_rn(X.a, by), I[r][1]));
-                        v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, ay), I[r][2]));
-                        v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, by), I[r][3]));
-                        if (COMPOSITE) v = __fadd_rn(cin[r], __fmul_rn(z, v));  // :724-726
-                        orow[r * g.Wo] = v;
+                    for (int r = 0; r < kFwdRB; ++r) {
+                        if (r < nb) {
+                            const int4 cy = rows[i0 + r];
+                            const float ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
+                            // transformer.py:112-116
+                            float v = __fadd_rn(__fmul_rn(__fmul_rn(X.a, ay), I[r][0]), __fmul_rn(__fmul_rn(X.a, by), I[r][1]));
+                            v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, ay), I[r][2]));
+                            v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, by), I[r][3]));
+                            if (COMPOSITE) v = __fadd_rn(cin[r], __fmul_rn(z, v));  // :724-726
+                            orow[r * g.Wo] = v;
+                        }
                     }
-                    orow += RB * g.Wo;
-                    if (COMPOSITE) crow += RB * g.Wo;
-                }
-                for (; i < nrows; ++i) {
-                    const int4 cy = rows[i];
-                    const float ay = __int_as_float(cy.z), by = __int_as_float(cy.w);
-                    const float Ia = ldg_f32(Ux0 + (unsigned)cy.x), Ib = ldg_f32(Ux0 + (unsigned)cy.y);
-                    const float Ic = ldg_f32(Ux1 + (unsigned)cy.x), Id = ldg_f32(Ux1 + (unsigned)cy.y);
-                    float v = __fadd_rn(__fmul_rn(__fmul_rn(X.a, ay), Ia), __fmul_rn(__fmul_rn(X.a, by), Ib));
-                    v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, ay), Ic));
-                    v = __fadd_rn(v, __fmul_rn(__fmul_rn(X.b, by), Id));
-                    if (COMPOSITE) {
-                        v = __fadd_rn(*crow, __fmul_rn(z, v));
-                        crow += g.Wo;
-                    }
-                    *orow = v;
-                    orow += g.Wo;
+                    orow += kFwdRB * g.Wo;
+                    if (COMPOSITE) crow += kFwdRB * g.Wo;
                 }
             }
             continue;
         }
-        // ---- general affine theta and/or several channels: per-pixel evaluation -------------------------
-        for (int j0 = 0; j0 < g.Wo; j0 += 32) {
-            const int j = j0 + lane;
-            if (j >= g.Wo) continue;
-            for (int i = 0; i < g.Ho; ++i) {
-                Axis X, Y;
-                taps_general(th, g, i, j, X, Y);
-                const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
-                const long long n = (long long)i * g.Wo + j;
-                if (r0 == r1) {
-                    if (COMPOSITE) {
-                        if (!inplace) ob[n] = __fadd_rn(cb[n], 0.0f);
-                    } else {
-                        for (int c = 0; c < C; ++c) ob[n * C + c] = 0.0f;
-                    }
-                    continue;
-                }
-                // transformer.py:112-115
-                const float wa = __fmul_rn(X.a, Y.a), wb = __fmul_rn(X.a, Y.b), wc = __fmul_rn(X.b, Y.a), wd = __fmul_rn(X.b, Y.b);
-                const float* pa = Ub + (long long)(r0 + X.c0) * C;
-                const float* pb = Ub + (long long)(r1 + X.c0) * C;
-                const float* pc = Ub + (long long)(r0 + X.c1) * C;
-                const float* pd = Ub + (long long)(r1 + X.c1) * C;
-                for (int c = 0; c < C; ++c) {
-                    // transformer.py:116  add_n in list order
-                    float v = __fadd_rn(__fmul_rn(wa, __ldg(pa + c)), __fmul_rn(wb, __ldg(pb + c)));
-                    v = __fadd_rn(v, __fmul_rn(wc, __ldg(pc + c)));
-                    v = __fadd_rn(v, __fmul_rn(wd, __ldg(pd + c)));
-                    if (COMPOSITE)
-                        ob[n] = __fadd_rn(cb[n], __fmul_rn(z, v));  // :724-726
-                    else
-                        ob[n * C + c] = v;
-                }
-            }
-        }
+        // ---- general affine theta and/or several channels: per-pixel evaluation (cold, out of line) ------
+        fwd_general_image<COMPOSITE>(Ub, ob, cb, th.t[0], th.t[1], th.t[2], th.t[3], th.t[4], th.t[5], z, inplace, lane, g.Hs,
+                                     g.Ws, g.C, g.Ho, g.Wo, g.step_w, g.step_h, g.wsc, g.hsc);
     }
 }
 
@@ -249,7 +287,7 @@ __global__ void __launch_bounds__(kWarpThreads) stn_fwd_warp_kernel(const FwdArg
 // ga [kBwdRB][Wo+1] | gb [kBwdRB][Wo+1]   (column Wo of every ga/gb row is a zero slot)
 // (rounded up to a multiple of 4 words so every warp's int4 tables stay 16-byte aligned)
 __host__ __device__ inline int bwd_warp_smem_words(const Geo& g) {
-    return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * 4 * (g.Wo + 1) + 3) & ~3;  // 4 = kBwdRB
+    return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * MOG_BWD_RB * (g.Wo + 1) + 3) & ~3;
 }
 
 template <int NXC>
@@ -266,10 +304,78 @@ __device__ __forceinline__ void emit_px(char* p, float v, bool ok, bool first) {
     }
 }
 
-constexpr int kBwdRB = 4;  // rows per batch of the streaming backward
+
+// General affine theta and/or several channels: warp-local zero fill of this image's dU, then L2 atomics
+// (red.global.add.f32) on its own lines; dtheta/dz by warp shuffles.  Out of line (cold path).
+template <bool COMPOSITE>
+__device__ __noinline__ void bwd_general_image(const float* __restrict__ Ub, float* __restrict__ dUb,
+                                               const float* __restrict__ gb, float* __restrict__ dtheta_b,
+                                               float* __restrict__ dz_b, float t0, float t1, float t2, float t3, float t4,
+                                               float t5, float z, bool first_write, int lane, int Hs, int Ws, int C,
+                                               int Ho, int Wo, float step_w, float step_h, float wsc, float hsc) {
+    Theta th;
+    th.t[0] = t0; th.t[1] = t1; th.t[2] = t2; th.t[3] = t3; th.t[4] = t4; th.t[5] = t5;
+    Geo g;
+    g.Hs = Hs; g.Ws = Ws; g.C = C; g.Ho = Ho; g.Wo = Wo; g.N = Ho * Wo; g.S = Hs * Ws;
+    g.step_w = step_w; g.step_h = step_h; g.wsc = wsc; g.hsc = hsc; g.magic_wo = 0;
+    const int SC = g.S * C;
+    float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (dUb && first_write) {
+        for (int k = lane; k < SC; k += 32) dUb[k] = 0.0f;
+        __syncwarp();
+    }
+    for (int j0 = 0; j0 < g.Wo; j0 += 32) {
+        const int j = j0 + lane;
+        if (j >= g.Wo) continue;
+        const float xt = lin_at(j, g.step_w);
+        for (int i = 0; i < g.Ho; ++i) {
+            Axis X, Y;
+            taps_general(th, g, i, j, X, Y);
+            // Out of range on an axis: the two taps alias one pixel with weights +w/-w, so every
+            // gradient contribution cancels in exact arithmetic (DESIGN.md "borders").
+            if (X.c0 == X.c1 || Y.c0 == Y.c1) continue;
+            const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
+            const int ia = (r0 + X.c0) * C, ib = (r1 + X.c0) * C, ic = (r0 + X.c1) * C, id = (r1 + X.c1) * C;
+            const float wa = X.a * Y.a, wb = X.a * Y.b, wc = X.b * Y.a, wd = X.b * Y.b;
+            float sx = 0.f, sy = 0.f;
+            const long long n = (long long)i * g.Wo + j;
+            for (int c = 0; c < C; ++c) {
+                const float gc = __ldg(gb + n * C + c);
+                const float gv = COMPOSITE ? gc * z : gc;
+                const float Ia = __ldg(Ub + ia + c), Ib = __ldg(Ub + ib + c);
+                const float Ic = __ldg(Ub + ic + c), Id = __ldg(Ub + id + c);
+                if (dUb) {
+                    atomicAdd(dUb + ia + c, wa * gv);
+                    atomicAdd(dUb + ib + c, wb * gv);
+                    atomicAdd(dUb + ic + c, wc * gv);
+                    atomicAdd(dUb + id + c, wd * gv);
+                }
+                sx += gv * (Y.a * (Ic - Ia) + Y.b * (Id - Ib));
+                sy += gv * (X.a * (Ib - Ia) + X.b * (Id - Ic));
+                if (COMPOSITE) p[6] += gc * (wa * Ia + wb * Ib + wc * Ic + wd * Id);
+            }
+            const float yt = lin_at(i, g.step_h);
+            p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
+            p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
+        }
+    }
+    __syncwarp();
+    const float half_wsc = g.wsc * 0.5f, half_hsc = g.hsc * 0.5f;
+    p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
+    p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
+    if (lane == 0) {
+        if (dtheta_b) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dtheta_b[k] = p[k];
+        }
+        if (COMPOSITE && dz_b) *dz_b = p[6];
+    }
+}
 
 template <bool COMPOSITE, int NXC>
-__global__ void __launch_bounds__(kWarpThreads, 2) stn_bwd_warp_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kernel(const BwdArgs a) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
@@ -311,47 +417,13 @@ __global__ void __launch_bounds__(kWarpThreads, 2) stn_bwd_warp_kernel(const Bwd
             if (!active) {
                 if (dUb && !dU_started) fill_zero(dUb, 0, SC, lane);
             } else if (!sep) {
-                // ---------- general affine: warp-local zero fill, then L2 atomics on this image's lines ----
-                if (dUb && !dU_started) {
-                    for (int k = lane; k < SC; k += 32) dUb[k] = 0.0f;
-                    __syncwarp();
-                }
-                for (int j0 = 0; j0 < g.Wo; j0 += 32) {
-                    const int j = j0 + lane;
-                    if (j >= g.Wo) continue;
-                    const float xt = lin_at(j, g.step_w);
-                    for (int i = 0; i < g.Ho; ++i) {
-                        Axis X, Y;
-                        taps_general(th, g, i, j, X, Y);
-                        // Out of range on an axis: the two taps alias one pixel with weights +w/-w, so every
-                        // gradient contribution cancels in exact arithmetic (DESIGN.md "borders").
-                        if (X.c0 == X.c1 || Y.c0 == Y.c1) continue;
-                        const int r0 = Y.c0 * g.Ws, r1 = Y.c1 * g.Ws;
-                        const int ia = (r0 + X.c0) * C, ib = (r1 + X.c0) * C, ic = (r0 + X.c1) * C, id = (r1 + X.c1) * C;
-                        const float wa = X.a * Y.a, wb = X.a * Y.b, wc = X.b * Y.a, wd = X.b * Y.b;
-                        float sx = 0.f, sy = 0.f;
-                        const long long n = (long long)i * g.Wo + j;
-                        for (int c = 0; c < C; ++c) {
-                            const float gc = __ldg(gb + n * C + c);
-                            const float gv = COMPOSITE ? gc * z : gc;
-                            const float Ia = __ldg(Ub + ia + c), Ib = __ldg(Ub + ib + c);
-                            const float Ic = __ldg(Ub + ic + c), Id = __ldg(Ub + id + c);
-                            if (dUb) {
-                                atomicAdd(dUb + ia + c, wa * gv);
-                                atomicAdd(dUb + ib + c, wb * gv);
-                                atomicAdd(dUb + ic + c, wc * gv);
-                                atomicAdd(dUb + id + c, wd * gv);
-                            }
-                            sx += gv * (Y.a * (Ic - Ia) + Y.b * (Id - Ib));
-                            sy += gv * (X.a * (Ib - Ia) + X.b * (Id - Ic));
-                            if (COMPOSITE) p[6] += gc * (wa * Ia + wb * Ib + wc * Ic + wd * Id);
-                        }
-                        const float yt = lin_at(i, g.step_h);
-                        p[0] += sx * xt; p[1] += sx * yt; p[2] += sx;
-                        p[3] += sy * xt; p[4] += sy * yt; p[5] += sy;
-                    }
-                }
-                __syncwarp();
+                // ---------- general affine / multi-channel: cold, out of line (writes dtheta/dz itself) ----
+                bwd_general_image<COMPOSITE>(Ub, dUb, gb, a.dtheta ? a.dtheta + 6 * b : nullptr,
+                                             (COMPOSITE && a.dz) ? a.dz + b : nullptr, th.t[0], th.t[1], th.t[2], th.t[3],
+                                             th.t[4], th.t[5], z, !dU_started, lane, g.Hs, g.Ws, g.C, g.Ho, g.Wo, g.step_w,
+                                             g.step_h, g.wsc, g.hsc);
+                dU_started = true;
+                continue;
             } else {
                 // ---------- separable: gather form, streaming over rows ----------------------------------
                 // Only in-range rows/columns contribute (out-of-range taps cancel, see above); both form one
@@ -430,8 +502,9 @@ __global__ void __launch_bounds__(kWarpThreads, 2) stn_bwd_warp_kernel(const Bwd
                             float gq[kBwdRB], I[kBwdRB][4];
 #pragma unroll
                             for (int r = 0; r < kBwdRB; ++r) {
-                                if (r < nb) {
-                                    const int i = ascending ? ilo + ii0 + r : ihi - ii0 - r;
+                                {
+                                    const int rr = min(r, nb - 1);  // tail rows re-load the last valid row
+                                    const int i = ascending ? ilo + ii0 + rr : ihi - ii0 - rr;
                                     cy[r] = s_row[i];
                                     gq[r] = __ldg(gb + i * g.Wo + j);
                                     const char* pa = Ubc + (unsigned)(cy[r].x + cj.x);
@@ -521,10 +594,6 @@ __global__ void __launch_bounds__(kWarpThreads, 2) stn_bwd_warp_kernel(const Bwd
                     }
                 }
                 // scale: dx_s = dx*(Ws-1.001)/2, dy_s = dy*(Hs-1.001)/2   (transformer.py:75-76)
-                p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
-                p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
-            }
-            if (active && !sep) {
                 p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
                 p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
             }
