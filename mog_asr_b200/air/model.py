@@ -1,0 +1,287 @@
+"""AIR-pPrior / AIR-ASR model (training graph) re-hosted in PyTorch.
+
+Follows ``/root/reference/air/air_number_bbox_location.py`` (``AIRModel._create_model``, ``:384-1122``) op for
+op; the three places where the reference touches the hot path go through an injectable ``ops`` object:
+
+  * read    ``:511-542``  ``ops.transformer(images[B,cs,cs,1], theta_r, (ws, ws))``
+  * write + composite ``:563-600,:718-727``  ``ops.write_composite(canvas, vae_recon, theta_w, z_pres, stop_sum, thr)``
+  * ASR regularisers ``:645-681,:970-1069``  ``ops.asr(cfg, log_odds[B,T], shifts[B,T,2], scales[B,T,1], ...)``
+
+``CudaOps`` (default) binds them to libmogstn's kernels.  The dense layers, LSTM cells and the elementwise
+KL / Concrete math stay in PyTorch (cuBLAS GEMMs; SURVEY 2.1 marks them out of scope as kernels).
+
+Random draws (TF's ``random_normal`` / ``random_uniform`` streams cannot be reproduced) come from a
+``noise`` callback so that a step can be replayed with identical noise on another implementation.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class AIRConfig:
+    """Keyword arguments of the reference ``AIRModel`` as ``train_air_pr.py:174-212`` passes them."""
+    canvas_size: int = 50
+    windows_size: int = 28
+    max_steps: int = 6
+    rnn_units: int = 256
+    vae_latent_dimensions: int = 50
+    vae_recognition_units: Sequence[int] = (512, 256)
+    vae_generative_units: Sequence[int] = (256, 512)
+    scale_hidden_units: int = 64
+    shift_hidden_units: int = 64
+    z_pres_hidden_units: int = 64
+    scale_prior_mean: float = -1.0          # fix_scale_distribution=True (:74-76)
+    scale_prior_variance: float = 0.05
+    vae_prior_mean: float = 0.0
+    vae_prior_variance: float = 1.0
+    vae_likelihood_std: float = 0.0
+    z_pres_temperature: float = 0.1         # -zt
+    stopping_threshold: float = 0.9
+    learning_rate: float = 1e-4
+    gradient_clipping_norm: float = 1.0
+    constrains_num: Sequence[int] = field(default_factory=lambda: [1, 3])   # digits of -dn
+    constrains_num_gamma: float = 0.0            # -gn
+    constrains_margin_gamma: float = 0.0         # -gm
+    constrains_num_element_gamma: float = 0.0    # -gne
+    constrains_bbox_gamma: float = 0.0           # -gb
+    constrains_sharesize_gamma: float = 0.0      # -gs
+    constrains_area_gamma: float = 0.0           # -ga
+    constrains_area_minmax: Sequence[float] = (17.0, 23.0)
+    fix_steps: Optional[int] = None              # the count when -dn has one digit (train_air_pr.py:212)
+    always_max_steps: bool = False               # run max_steps iterations regardless of the `any` test (:386-390)
+
+
+def config_from_flags(data="mnist", dn="13", ds="", gn=0.0, gm=0.0, gne=0.0, gb=0.0, gs=0.0, ga=0.0, zt=0.1, **kw):
+    """The derivations of ``train_air_pr.py:67-98,:204-212`` from its command-line flags."""
+    counts = [int(c) for c in dn]
+    if data.lower() == "mnist":
+        cs, mm = 50, ((11, 15) if "bbox" in ds else (17, 23))
+    else:
+        cs, mm = 64, ((12, 15) if "bbox" in ds else (20, 25))
+    return AIRConfig(canvas_size=cs, constrains_num=counts, constrains_num_gamma=gn, constrains_margin_gamma=gm,
+                     constrains_num_element_gamma=gne, constrains_bbox_gamma=gb, constrains_sharesize_gamma=gs,
+                     constrains_area_gamma=ga, constrains_area_minmax=mm, z_pres_temperature=zt,
+                     fix_steps=counts[0] if len(counts) == 1 else None, **kw)
+
+
+class CudaOps:
+    """The hot-path operators bound to libmogstn (the product path)."""
+
+    def __init__(self, process_group=None, global_batch=None):
+        self.process_group, self.global_batch = process_group, global_batch
+
+    def transformer(self, U, theta, out_size):
+        from ..transformer import transformer
+        return transformer(U, theta, out_size)
+
+    def write_composite(self, canvas, window, theta, z_pres, stop_sum, threshold):
+        from ..composite import write_composite
+        return write_composite(canvas, window, theta, z_pres, stop_sum, threshold)
+
+    def asr(self, cfg: AIRConfig, log_odds, shifts, scales):
+        from ..asr import AsrRegulariser, asr_regularisers
+        reg = AsrRegulariser(
+            canvas_size=cfg.canvas_size, max_steps=cfg.max_steps, constrains_num=list(cfg.constrains_num),
+            constrains_num_gamma=cfg.constrains_num_gamma, constrains_margin_gamma=cfg.constrains_margin_gamma,
+            constrains_num_element_gamma=cfg.constrains_num_element_gamma, constrains_bbox_gamma=cfg.constrains_bbox_gamma,
+            constrains_sharesize_gamma=cfg.constrains_sharesize_gamma, constrains_area_gamma=cfg.constrains_area_gamma,
+            constrains_area_minmax=cfg.constrains_area_minmax)
+        return asr_regularisers(reg, log_odds, shifts, scales, process_group=self.process_group,
+                                global_batch=self.global_batch)
+
+
+class LSTMCellTF(nn.Module):
+    """``tf.nn.rnn_cell.LSTMCell(units)`` (:865-872): one kernel ``[in+units, 4*units]``, gate order i, j, f, o,
+    ``forget_bias = 1.0`` added at run time, glorot-uniform kernel, zero bias  [TF-1.12 defaults]."""
+
+    def __init__(self, input_size: int, units: int):
+        super().__init__()
+        self.units = units
+        self.kernel = nn.Parameter(torch.empty(input_size + units, 4 * units))
+        self.bias = nn.Parameter(torch.zeros(4 * units))
+        nn.init.xavier_uniform_(self.kernel)
+
+    def forward(self, x, state):
+        c, h = state
+        gates = torch.addmm(self.bias, torch.cat([x, h], 1), self.kernel)
+        i, j, f, o = gates.chunk(4, 1)
+        c2 = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+        h2 = torch.sigmoid(o) * torch.tanh(c2)
+        return h2, (c2, h2)
+
+
+def _dense(i, o):
+    """``tf.layers.dense`` / ``layers.fully_connected`` defaults: glorot-uniform kernel, zero bias."""
+    l = nn.Linear(i, o)
+    nn.init.xavier_uniform_(l.weight)
+    nn.init.zeros_(l.bias)
+    return l
+
+
+class _MeanVar(nn.Module):
+    """Two 2-layer heads (mean, log-variance) of the shift / scale blocks (:424-460, :472-481)."""
+
+    def __init__(self, in_dim, hidden, out_dim, skip_dim=0):
+        super().__init__()
+        self.hm, self.m = _dense(in_dim + skip_dim, hidden), _dense(hidden + skip_dim, out_dim)
+        self.hv, self.v = _dense(in_dim + skip_dim, hidden), _dense(hidden + skip_dim, out_dim)
+
+    def forward(self, x, skip=None):
+        cat = (lambda a: torch.cat([a, skip], -1)) if skip is not None else (lambda a: a)
+        mean = self.m(cat(F.relu(self.hm(cat(x)))))
+        logvar = self.v(cat(F.relu(self.hv(cat(x)))))
+        return mean, logvar
+
+
+class AIRModel(nn.Module):
+    """Training graph of the reference ``AIRModel`` (``train=True``)."""
+
+    def __init__(self, cfg: AIRConfig, ops=None):
+        super().__init__()
+        self.cfg, self.ops = cfg, (ops if ops is not None else CudaOps())
+        H, L, cs2, ws2 = cfg.rnn_units, cfg.vae_latent_dimensions, cfg.canvas_size ** 2, cfg.windows_size ** 2
+        self.infer_cell = LSTMCellTF(cs2 + L + 3, H)                        # :413-422
+        self.inf_shift = _MeanVar(H, cfg.shift_hidden_units, 2)             # :424-437
+        self.inf_scale = _MeanVar(H, cfg.scale_hidden_units, 1, skip_dim=2)  # :439-460
+        self.gen_cell = LSTMCellTF(L + 3, H)                                # :465-470
+        self.gen_shift = _MeanVar(H, cfg.shift_hidden_units, 2)             # :472-481
+        r, gdim = list(cfg.vae_recognition_units), list(cfg.vae_generative_units)
+        self.vae_rec = nn.ModuleList([_dense(a, b) for a, b in zip([ws2] + r[:-1], r)])          # vae.py:16-19
+        self.vae_rec_mean, self.vae_rec_logvar = _dense(r[-1], L), _dense(r[-1], L)              # vae.py:21-26
+        self.vae_gen = nn.ModuleList([_dense(a, b) for a, b in zip([L] + gdim[:-1], gdim)])      # vae.py:34-37
+        self.vae_gen_mean = _dense(gdim[-1], ws2)                                                # vae.py:39-41
+        if cfg.fix_steps is None:
+            self.z_prior_h, self.z_prior = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)  # :609-615
+        self.z_post_h, self.z_post = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)        # :620-623
+
+    # ---- pieces -------------------------------------------------------------------------------------------
+    def _vae(self, window, eps):
+        """air/vae.py:5-48 (softplus hidden layers, sigmoid output; likelihood_std = 0 drops the second noise)."""
+        x = window
+        for l in self.vae_rec:
+            x = F.softplus(l(x))
+        mean, logvar = self.vae_rec_mean(x), self.vae_rec_logvar(x)
+        latent = mean + eps * torch.sqrt(torch.exp(logvar))
+        x = latent
+        for l in self.vae_gen:
+            x = F.softplus(l(x))
+        return torch.sigmoid(self.vae_gen_mean(x)), mean, logvar, latent
+
+    @staticmethod
+    def _concrete_kl(y, prior_lo, post_lo, temp, eps=10e-10):
+        """air/concrete.py:30-64 with prior temperature == posterior temperature (:690-696)."""
+        def logp(lo):
+            lse = torch.logsumexp(torch.stack([torch.zeros_like(y), -y * temp + lo]), 0)
+            return math.log(temp + eps) - y * (temp + 1) + lo - 2.0 * lse
+        return logp(post_lo) - logp(prior_lo)
+
+    # ---- the training graph ----------------------------------------------------------------------------------
+    def forward(self, images, noise: Optional[Callable] = None, any_reduce: Optional[Callable] = None,
+                global_batch: Optional[int] = None, recon_loss_fn: Optional[Callable] = None):
+        """images ``[B, cs*cs]`` in [0,1].  ``noise(kind, step, shape)`` supplies N(0,1) ('shift','scale','vae')
+        or U(0,1) ('concrete') draws.  ``any_reduce(flag_tensor)`` makes the loop condition global across ranks.
+        ``recon_loss_fn(images, clipped_canvas) -> [B]`` replaces the reference's cross-entropy (:954-959); it
+        exists for tests only: the reference term has gradients of 1e10 wherever the canvas is exactly 0 under
+        an object pixel, which amplifies fp32 rounding noise of *any* implementation beyond comparison.
+        Returns a dict with ``loss`` (differentiable) and the reference's log variables."""
+        cfg = self.cfg
+        dev, dt = images.device, images.dtype
+        B = images.shape[0]
+        cs, ws, thr, temp = cfg.canvas_size, cfg.windows_size, cfg.stopping_threshold, cfg.z_pres_temperature
+        if noise is None:
+            noise = lambda kind, step, shape: (torch.rand(shape, device=dev, dtype=dt) if kind == "concrete"
+                                               else torch.randn(shape, device=dev, dtype=dt))
+        H, L = cfg.rnn_units, cfg.vae_latent_dimensions
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+        stop_sum = z(B)
+        inf_state, gen_state = (z(B, H), z(B, H)), (z(B, H), z(B, H))
+        gen_prev_out, prev_latent, prev_ss = z(B, H), z(B, L), z(B, 3)
+        canvas = z(B, cs, cs)
+        digits = torch.zeros(B, dtype=torch.int32, device=dev)
+        kl = {k: [] for k in ("z_pres_kl", "scale_kl", "shift_kl", "vae_kl")}
+        lo_list, sh_list, sc_list = [], [], []
+        g_scale_lv = math.log(cfg.scale_prior_variance)
+        images4 = images.reshape(B, cs, cs, 1)
+
+        step = 0
+        while step < cfg.max_steps:
+            if not cfg.always_max_steps and step > 0:        # cond (:386-390); step 0 always runs (stop_sum = 0)
+                flag = (stop_sum < thr).any()
+                if any_reduce is not None:
+                    flag = any_reduce(flag)
+                if not bool(flag):
+                    break
+            out, inf_state = self.infer_cell(torch.cat([images, prev_latent, prev_ss], -1), inf_state)      # :413-422
+            sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
+            sh_var = torch.exp(sh_lv)
+            shift_latent = sh_mean + noise("shift", step, (B, 2)) * torch.sqrt(sh_var)                      # :433-434
+            inf_shift = torch.tanh(shift_latent)                                                            # :435
+            sc_mean, sc_lv = self.inf_scale(out, shift_latent)                                              # :439-455
+            sc_var = torch.exp(sc_lv)
+            scale_latent = sc_mean + noise("scale", step, (B, 1)) * torch.sqrt(sc_var)                      # :456-457
+            inf_scale = torch.sigmoid(scale_latent)                                                         # :458
+            ss_latent = torch.cat([shift_latent, scale_latent], -1)                                         # :463
+            gen_out, gen_state = self.gen_cell(torch.cat([prev_latent, prev_ss], -1), gen_state)            # :465-470
+            g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
+            g_sh_var = torch.exp(g_sh_lv)
+
+            s, x, y = inf_scale[:, 0], inf_shift[:, 0], inf_shift[:, 1]
+            zero = torch.zeros_like(s)
+            theta_r = torch.stack([s, zero, x, zero, s, y], 1)                                              # :511-531
+            window = self.ops.transformer(images4, theta_r, (ws, ws))[:, :, :, 0]                           # :534-542
+            recon, v_mean, v_lv, v_latent = self._vae(window.reshape(B, ws * ws), noise("vae", step, (B, L)))  # :544-553
+            theta_w = torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1)                        # :563-584
+
+            if cfg.fix_steps is not None:                                                                   # :604-608
+                prior_lo = torch.full((B,), 100.0 if step < cfg.fix_steps else -100.0, device=dev, dtype=dt)
+            else:
+                prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev_out)))[:, 0]                         # :609-615
+            post_lo = self.z_post(F.relu(self.z_post_h(out)))[:, 0]                                         # :620-623
+            u = noise("concrete", step, (B,))
+            y_pre = (post_lo + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temp                  # concrete.py:20-27
+            z_pres = torch.sigmoid(y_pre)                                                                   # :631
+            z_kl = self._concrete_kl(y_pre, prior_lo, post_lo, temp)                                        # :690-696
+            active_prev = stop_sum < thr                                                                    # previous stop_sum (:698-702)
+            kl["z_pres_kl"].append(torch.where(active_prev, z_kl, torch.zeros_like(z_kl)))
+            stop_sum = stop_sum + (1.0 - z_pres)                                                            # :712
+            active = stop_sum < thr
+            digits = digits + active.to(torch.int32)                                                        # :715-716
+            canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
+
+            scale_kl = 0.5 * (g_scale_lv - sc_lv - 1.0 + sc_var / cfg.scale_prior_variance
+                              + (sc_mean - cfg.scale_prior_mean) ** 2 / cfg.scale_prior_variance).sum(-1)   # :731-736
+            shift_kl = 0.5 * (g_sh_lv - sh_lv - 1.0 + sh_var / g_sh_var + (sh_mean - g_sh_mean) ** 2 / g_sh_var).sum(-1)  # :750-755
+            vae_kl = 0.5 * (math.log(cfg.vae_prior_variance) - v_lv - 1.0 + torch.exp(v_lv) / cfg.vae_prior_variance
+                            + (v_mean - cfg.vae_prior_mean) ** 2 / cfg.vae_prior_variance).sum(1)           # :769-774
+            for k, v in (("scale_kl", scale_kl), ("shift_kl", shift_kl), ("vae_kl", vae_kl)):
+                kl[k].append(torch.where(active, v, torch.zeros_like(v)))                                   # masks use the NEW stop_sum
+            lo_list.append(post_lo); sh_list.append(inf_shift); sc_list.append(inf_scale)
+            gen_prev_out, prev_latent, prev_ss = gen_out, v_latent, ss_latent
+            step += 1
+
+        T = step
+        elbo = sum(torch.stack(v, 1).sum(-1) for v in kl.values())                                          # :930-935
+        recon_c = torch.clamp(canvas.reshape(B, cs * cs), 0.0, 1.0)                                         # :947-948
+        if recon_loss_fn is None:
+            rec_loss = -(images * torch.log(recon_c + 1e-10) + (1.0 - images) * torch.log(1.0 - recon_c + 1e-10)).sum(1)  # :954-959
+        else:
+            rec_loss = recon_loss_fn(images, recon_c)
+        elbo = elbo + rec_loss                                                                              # :968
+        log_odds = torch.stack(lo_list, 1)
+        shifts, scales = torch.stack(sh_list, 1), torch.stack(sc_list, 1)
+        per_image, margin, comps = self.ops.asr(cfg, log_odds, shifts, scales)                              # :645-681,:970-1069
+        nglobal = B if global_batch is None else global_batch
+        # loss = mean_b(elbo + pr_loss + num_element_min) + num_marginal_loss  (:1078-1079); under data
+        # parallelism each rank holds sum_local / B_global and the gradient all-reduce restores the mean
+        loss = (elbo + per_image).sum() / nglobal + margin
+        return dict(loss=loss, elbo=elbo.detach(), recon=rec_loss.detach(), steps=T, rec_num_digits=digits,
+                    margin=margin.detach(), per_image_reg=per_image.detach(), components=comps,
+                    rec_scales=scales.detach(), rec_shifts=shifts.detach(), z_pres_probs=torch.sigmoid(log_odds).detach(),
+                    reconstruction=recon_c.detach())

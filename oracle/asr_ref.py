@@ -57,14 +57,15 @@ def asr_terms(log_odds, shifts, scales, *, canvas_size, counts, max_steps, gamma
         ent = P * torch.nn.functional.softplus(-log_odds) + (1.0 - P) * torch.nn.functional.softplus(log_odds)
         pr_num = (ent * gamma_num).sum(-1)
     else:
-        pr_num = torch.zeros(B, dtype=dt)
+        pr_num = torch.zeros(B, dtype=dt, device=log_odds.device)
 
     # ---- count penalties (:970-1015); both gated by gamma_margin > 1e-8 (:973)
-    margin = torch.zeros((), dtype=dt)
-    elem = torch.zeros(B, dtype=dt)
+    dev = log_odds.device
+    margin = torch.zeros((), dtype=dt, device=dev)
+    elem = torch.zeros(B, dtype=dt, device=dev)
     if gamma_margin > 1e-8:
         K = len(counts)
-        obj = torch.zeros(K, max_steps, dtype=dt)
+        obj = torch.zeros(K, max_steps, dtype=dt, device=dev)
         for k, c in enumerate(counts):
             obj[k, :c] = 1.0                                               # :974-976
         mobj = obj.mean(0)                                                 # :979
@@ -91,7 +92,7 @@ def asr_terms(log_odds, shifts, scales, *, canvas_size, counts, max_steps, gamma
     # tf.maximum(x_diff, y_diff): gradient to x_diff when x_diff >= y_diff  [TF-1.12 assumed]
     maxd = torch.where(xd >= yd, xd, yd)
     smean = (px[:, :, None] + px[:, None, :]) / 2.0
-    over = _tf_max0(smean - maxd) * (1.0 - torch.eye(T, dtype=dt))
+    over = _tf_max0(smean - maxd) * (1.0 - torch.eye(T, dtype=dt, device=dev))
     overlap = over.sum((-1, -2))
 
     pr_loss = pr_num + gamma_area * area + gamma_bbox * (overlap + out) + gamma_size * size

@@ -14,29 +14,30 @@ from __future__ import annotations
 import torch
 
 
-def _linspace(num: int, dtype) -> torch.Tensor:
+def _linspace(num: int, dtype, device="cpu") -> torch.Tensor:
     # transformer.py:126-128, TF-1.12 LinSpace recurrence evaluated in fp32 then widened
     if num == 1:
-        return torch.tensor([-1.0], dtype=dtype)
-    step = torch.tensor(2.0, dtype=torch.float32) / torch.tensor(float(num - 1), dtype=torch.float32)
-    i = torch.arange(num, dtype=torch.float32)
-    return (torch.tensor(-1.0, dtype=torch.float32) + step * i).to(dtype)
+        return torch.tensor([-1.0], dtype=dtype, device=device)
+    step = torch.tensor(2.0, dtype=torch.float32, device=device) / torch.tensor(float(num - 1), dtype=torch.float32, device=device)
+    i = torch.arange(num, dtype=torch.float32, device=device)
+    return (torch.tensor(-1.0, dtype=torch.float32, device=device) + step * i).to(dtype)
 
 
 def transformer(U: torch.Tensor, theta: torch.Tensor, out_size, name="SpatialTransformer", **kwargs):
-    """Differentiable restatement of transformer.py:18-175 (any float dtype; CPU)."""
+    """Differentiable restatement of transformer.py:18-175 from torch primitives (any float dtype, any device)."""
     dtype = U.dtype
     B, H, W, C = U.shape
     Ho, Wo = int(out_size[0]), int(out_size[1])
     theta = theta.reshape(-1, 2, 3).to(dtype)                                   # :144-145
-    lin_w, lin_h = _linspace(Wo, dtype), _linspace(Ho, dtype)
+    dev = U.device
+    lin_w, lin_h = _linspace(Wo, dtype, dev), _linspace(Ho, dtype, dev)
     x_t = lin_w[None, :].expand(Ho, Wo).reshape(-1)                             # :126-127,131
     y_t = lin_h[:, None].expand(Ho, Wo).reshape(-1)                             # :128-129,132
     x_s = (theta[:, 0, 0:1] * x_t + theta[:, 0, 1:2] * y_t) + theta[:, 0, 2:3]  # :159
     y_s = (theta[:, 1, 0:1] * x_t + theta[:, 1, 1:2] * y_t) + theta[:, 1, 2:3]
     f32 = torch.float32
-    wscale = (torch.tensor(float(W), dtype=f32) - torch.tensor(1.001, dtype=f32)).to(dtype)
-    hscale = (torch.tensor(float(H), dtype=f32) - torch.tensor(1.001, dtype=f32)).to(dtype)
+    wscale = (torch.tensor(float(W), dtype=f32, device=dev) - torch.tensor(1.001, dtype=f32, device=dev)).to(dtype)
+    hscale = (torch.tensor(float(H), dtype=f32, device=dev) - torch.tensor(1.001, dtype=f32, device=dev)).to(dtype)
     x = (x_s + 1.0) * wscale / 2.0                                              # :75
     y = (y_s + 1.0) * hscale / 2.0                                              # :76
     x0 = torch.floor(x.detach()).clamp(-1, W).long()                            # :79
@@ -45,7 +46,7 @@ def transformer(U: torch.Tensor, theta: torch.Tensor, out_size, name="SpatialTra
     y1 = y0 + 1                                                                 # :82
     x0, x1 = x0.clamp(0, W - 1), x1.clamp(0, W - 1)                             # :84-85
     y0, y1 = y0.clamp(0, H - 1), y1.clamp(0, H - 1)                             # :86-87
-    base = (torch.arange(B) * (H * W))[:, None]                                 # :88-90
+    base = (torch.arange(B, device=dev) * (H * W))[:, None]                                 # :88-90
     idx_a, idx_b = base + y0 * W + x0, base + y1 * W + x0                       # :91-94
     idx_c, idx_d = base + y0 * W + x1, base + y1 * W + x1                       # :95-96
     im_flat = U.reshape(-1, C)                                                  # :100

@@ -1,0 +1,58 @@
+"""Test-only ``ops`` object for ``AIRModel``: the three hot-path operators built from the oracle's torch-CPU
+restatements (``oracle/stn_ref_torch.py``, ``oracle/asr_ref.py``) and plain reference ops for the composite
+(``air/air_number_bbox_location.py:722-727``).  Lives under tests/ -- the product never sees it."""
+import torch
+import torch.distributed as dist
+
+from oracle import asr_ref, stn_ref_torch
+
+
+class OracleOps:
+    def __init__(self, process_group=None, global_batch=None):
+        self.pg, self.global_batch = process_group, global_batch
+
+    def transformer(self, U, theta, out_size):
+        return stn_ref_torch.transformer(U, theta, out_size)
+
+    def write_composite(self, canvas, window, theta, z_pres, stop_sum, threshold):
+        B, cs = canvas.shape[0], canvas.shape[1]
+        win = stn_ref_torch.transformer(window[..., None], theta, (cs, cs))[..., 0]
+        return canvas + torch.where((stop_sum < threshold)[:, None, None], z_pres[:, None, None] * win, torch.zeros_like(win))
+
+    def asr(self, cfg, log_odds, shifts, scales):
+        pbar = None
+        if cfg.constrains_margin_gamma > 1e-8:
+            psum = torch.sigmoid(log_odds).detach().sum(0)
+            n = log_odds.shape[0]
+            if self.pg is not None:
+                dist.all_reduce(psum, group=self.pg)
+                n = self.global_batch or n * dist.get_world_size(self.pg)
+            # value from the global sum, gradient through the local rows: d pbar / d P[b,t] = 1 / n_global
+            local = torch.sigmoid(log_odds).sum(0)
+            pbar = (psum - local.detach() + local) / n
+        r = asr_ref.asr_terms(log_odds, shifts, scales[..., 0], canvas_size=cfg.canvas_size, counts=list(cfg.constrains_num),
+                              max_steps=cfg.max_steps, gamma_num=cfg.constrains_num_gamma,
+                              gamma_margin=cfg.constrains_margin_gamma, gamma_elem=cfg.constrains_num_element_gamma,
+                              gamma_bbox=cfg.constrains_bbox_gamma, gamma_size=cfg.constrains_sharesize_gamma,
+                              gamma_area=cfg.constrains_area_gamma, area_minmax=tuple(cfg.constrains_area_minmax),
+                              batch_prob_mean=pbar)
+        comps = torch.stack([r[k] for k in ("pr_num", "num_min", "area", "out", "size", "overlap")], 1).detach()
+        return r["per_image"], r["margin"], comps
+
+
+class SeededNoise:
+    """noise(kind, step, shape) drawn on the CPU from a seed per (kind, step) for the *global* batch, then the
+    rank's rows are sliced out -- identical draws for any implementation / sharding."""
+
+    def __init__(self, seed, global_batch, lo=0, hi=None, device="cpu", dtype=torch.float32):
+        self.seed, self.B, self.lo, self.hi, self.device, self.dtype = seed, global_batch, lo, hi or global_batch, device, dtype
+
+    def __call__(self, kind, step, shape):
+        # numpy's generator: the draw must not depend on torch's intra-op thread count
+        import numpy as np
+        g = np.random.default_rng(self.seed * 1000 + {"shift": 1, "scale": 2, "vae": 3, "concrete": 4}[kind] * 100 + step)
+        full = (self.B,) + tuple(shape[1:])
+        t = g.random(full, dtype=np.float32) if kind == "concrete" else g.standard_normal(full, dtype=np.float32)
+        if kind == "concrete":
+            t = np.clip(t, 1e-4, 1 - 1e-4)
+        return torch.from_numpy(t[self.lo:self.hi]).to(self.device, self.dtype)
