@@ -49,6 +49,7 @@ def parse_args():
     p.add_argument("--regime", default="prior", choices=["prior", "full"])
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-train", action="store_true", help="skip the AIR-ASR training-step section")
     p.add_argument("--cpu-sample", type=int, default=1024, help="canvases in the CPU-baseline sample")
     p.add_argument("--sweep", action="store_true", help="run the whole config-5 sweep, write profiles/sweep_*.json")
     p.add_argument("--tag", default="", help="suffix for files written under profiles/")
@@ -316,6 +317,40 @@ def e2e_measure(a, dev, steps, warmup):
     return dt, h2d, d2h, AIR_STEPS * 2 * 2 * chunks
 
 
+def train_section(a, dev, world, pg, rank):
+    """Secondary metric of BASELINE.json: AIR-ASR training images/sec (configs 2-4) around the same kernels."""
+    from mog_asr_b200.air import bench_train
+    out = {}
+    r = bench_train.run("C4", dev, steps=10, warmup=3, process_group=pg, always_max_steps=True, graph=True)
+    out["C4_global4096"] = r
+    if world == 1:
+        for name in ("C2", "C3"):
+            out[name + "_graph"] = bench_train.run(name, dev, steps=10, warmup=3, always_max_steps=True, graph=True)
+            out[name + "_eager_reference_loop"] = bench_train.run(name, dev, steps=10, warmup=3)
+        if not a.no_cpu:
+            out["cpu_port_C2"] = train_cpu_baseline()
+    return out
+
+
+def train_cpu_baseline():
+    """C2 step (batch 64) with the oracle's operators on the host cores (torch-CPU, all threads)."""
+    import torch
+    from mog_asr_b200.air import Trainer, bench_train, config_from_flags
+    from oracle.air_ops import OracleOps
+    flags, gb = bench_train.CONFIGS["C2"]
+    cfg = config_from_flags(**flags)
+    tr = Trainer(cfg, "cpu", ops=OracleOps())
+    images = bench_train.synthetic_batch(cfg, gb, 0, "cpu")
+    tr.step(images)
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        tr.step(images)
+    dt = (time.perf_counter() - t0) / n
+    return dict(images_per_sec=gb / dt, ms_per_step=dt * 1e3, global_batch=gb, cores=torch.get_num_threads(), kind="port",
+                sample=f"{n} steps of config C2 (batch {gb}) with oracle/air_ops.py on torch-CPU")
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -409,16 +444,69 @@ def run_ours(a):
         if world == 1 and not a.no_cpu:
             cb, _ = cpu_measure(a, 3, 1, a.cpu_sample)
             line["cpu_baseline"] = cb
+    train = None
+    if not a.no_train:
+        train = train_section(a, dev, world, dist.group.WORLD if world > 1 else None, rank)
+    if rank == 0:
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def run_sweep(a):
+    """Every cell of BASELINE config 5 on one GPU: canvas {50,64,128,256} x glimpse {28,64} (glimpse < canvas),
+    theta regimes prior-like / full-cover, read and write directions; writes profiles/sweep_<tag>.json."""
+    import copy
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    peak, peak_src = peak_hbm()
+    rows = []
+    for canvas in (50, 64, 128, 256):
+        for glimpse in (28, 64):
+            if glimpse >= canvas:
+                continue
+            for regime in ("prior", "full"):
+                c = copy.copy(a)
+                c.canvas, c.glimpse, c.regime = canvas, glimpse, regime
+                wl = GpuWorkload(c, dev, seed=10)
+                for _ in range(3):
+                    wl.step()
+                torch.cuda.synchronize(dev)
+                events = {k: [] for k in wl.kinds}
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.steps):
+                    wl.step(events)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms = e0.elapsed_time(e1) / a.steps
+                kern_ms = {k: float(np.mean([x.elapsed_time(y) for x, y in events[k]])) for k in wl.kinds}
+                ab = wl.algorithmic_bytes()
+                row = dict(canvas=canvas, glimpse=glimpse, regime=regime, batch=c.batch, ms_per_step=ms,
+                           glimpses_per_sec=c.batch * 2 * AIR_STEPS / (ms * 1e-3),
+                           step_alg_gbs=sum(ab.values()) * AIR_STEPS / (ms * 1e-3) / 1e9,
+                           kernels={k: dict(us=kern_ms[k] * 1e3, alg_mb=ab[k] / 1e6, gbs=ab[k] / (kern_ms[k] * 1e-3) / 1e9,
+                                            frac=ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds})
+                row["step_frac"] = row["step_alg_gbs"] / peak
+                rows.append(row)
+                print(json.dumps(row), flush=True)
+                del wl
+                torch.cuda.empty_cache()
+    out = os.path.join(ROOT, "profiles", f"sweep_{a.tag or 'latest'}.json")
+    with open(out, "w") as f:
+        json.dump(dict(peak_gbs=peak, peak_source=peak_src, steps=a.steps, cells=rows), f, indent=1)
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.sweep:
+        run_sweep(a)
     else:
         run_ours(a)
 

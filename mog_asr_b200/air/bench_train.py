@@ -24,7 +24,7 @@ def synthetic_batch(cfg, batch, seed, device):
     return torch.tensor(np.clip(canv, 0.0, 1.0).reshape(batch, -1), device=device)
 
 
-def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=False):
+def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=False, graph=False):
     """Returns dict(images_per_sec, ms_per_step, global_batch, per_rank_batch, mean loop steps)."""
     flags, gbatch = CONFIGS[name]
     world = dist.get_world_size(process_group) if process_group is not None else 1
@@ -34,8 +34,12 @@ def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=F
     tr = Trainer(cfg, device, process_group=process_group, global_batch=gbatch)
     # a few distinct resident batches, cycled (the reference feeds from a shuffle queue)
     batches = [synthetic_batch(cfg, local, 100 * rank + k, device) for k in range(4)]
+    step_fn = tr.step
+    if graph:
+        tr.capture(local)
+        step_fn = tr.step_graph
     for k in range(warmup):
-        tr.step(batches[k % 4])
+        step_fn(batches[k % 4])
     torch.cuda.synchronize(device)
     if process_group is not None:
         dist.barrier(process_group)
@@ -43,7 +47,7 @@ def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=F
     T = 0
     e0.record()
     for k in range(steps):
-        T += tr.step(batches[k % 4])["steps"]
+        T += step_fn(batches[k % 4])["steps"]
     e1.record()
     torch.cuda.synchronize(device)
     ms = e0.elapsed_time(e1) / steps
@@ -53,4 +57,5 @@ def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=F
         ms = float(t.item())
     return dict(config=name, images_per_sec=gbatch / (ms * 1e-3), ms_per_step=ms, global_batch=gbatch,
                 per_rank_batch=local, n_gpus=world, mean_loop_steps=T / steps, grad_floats=tr.num_gradient_floats(),
-                mode="fixed max_steps" if always_max_steps else "reference loop condition (host-checked any)")
+                mode=("CUDA graph, fixed max_steps" if graph else "eager, fixed max_steps") if always_max_steps
+                else "eager, reference loop condition (host-checked any)")

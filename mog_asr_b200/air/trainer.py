@@ -41,6 +41,8 @@ class Trainer:
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
+        self.t_dev = torch.zeros((), dtype=torch.float64, device=self.device)
+        self.graph = None
         self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-8   # tf.train.AdamOptimizer defaults
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed + 1 + (dist.get_rank(process_group) if process_group is not None else 0))
@@ -74,7 +76,9 @@ class Trainer:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def postprocess_and_apply(self):
-        """:1100-1111 per-variable inf/nan -> 0 and clip_by_norm, then TF's Adam update."""
+        """:1100-1111 per-variable inf/nan -> 0 and clip_by_norm, then TF's Adam update
+        ``lr_t = lr*sqrt(1-b2^t)/(1-b1^t); var -= lr_t * m / (sqrt(v) + eps)``.  The step counter lives on the
+        device so the whole update is CUDA-graph capturable."""
         g = self.flat_grad
         torch.nan_to_num_(g, nan=0.0, posinf=0.0, neginf=0.0)
         c = self.cfg.gradient_clipping_norm
@@ -85,13 +89,44 @@ class Trainer:
             torch._foreach_mul_(self.grads, scales)
         self.t += 1
         b1, b2 = self.beta1, self.beta2
-        lr_t = self.cfg.learning_rate * (1.0 - b2 ** self.t) ** 0.5 / (1.0 - b1 ** self.t)
+        self.t_dev += 1.0
+        lr_t = self.cfg.learning_rate * torch.sqrt(1.0 - torch.pow(b2, self.t_dev)) / (1.0 - torch.pow(b1, self.t_dev))
         torch._foreach_mul_(self.m, b1); torch._foreach_add_(self.m, self.grads, alpha=1.0 - b1)
         torch._foreach_mul_(self.v, b2); torch._foreach_addcmul_(self.v, self.grads, self.grads, value=1.0 - b2)
         denom = torch._foreach_sqrt(self.v)
         torch._foreach_add_(denom, self.eps)
+        upd = torch._foreach_div(self.m, denom)
+        torch._foreach_mul_(upd, -lr_t.to(self.flat_grad.dtype))
         with torch.no_grad():
-            torch._foreach_addcdiv_(self.params, self.m, denom, value=-lr_t)
+            torch._foreach_add_(self.params, upd)
+
+    # ---- CUDA-graph mode: the ~1500 small launches of one step replayed as one graph ------------------------
+    def capture(self, batch_size: int):
+        """Capture forward + backward + all-reduce + update for a fixed local batch size.  Needs
+        ``cfg.always_max_steps`` (the reference's data-dependent trip count, :386-390, needs a host decision per
+        iteration and cannot be captured).  Noise comes from the default CUDA generator (graph-safe)."""
+        if not self.cfg.always_max_steps:
+            raise ValueError("graph capture needs AIRConfig.always_max_steps=True")
+        cs2 = self.cfg.canvas_size ** 2
+        self.static_images = torch.zeros((batch_size, cs2), device=self.device)
+        noise = lambda kind, step, shape: (torch.rand(shape, device=self.device) if kind == "concrete"
+                                           else torch.randn(shape, device=self.device))
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self.step(self.static_images, noise=noise)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = self.step(self.static_images, noise=noise)
+        return self
+
+    def step_graph(self, images):
+        self.static_images.copy_(images, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
 
     def step(self, images, noise=None):
         out = self.forward_backward(images, noise)

@@ -1,6 +1,8 @@
-"""Test-only ``ops`` object for ``AIRModel``: the three hot-path operators built from the oracle's torch-CPU
-restatements (``oracle/stn_ref_torch.py``, ``oracle/asr_ref.py``) and plain reference ops for the composite
-(``air/air_number_bbox_location.py:722-727``).  Lives under tests/ -- the product never sees it."""
+"""ORACLE (test infrastructure, NOT product code) -- an ``ops`` object for ``mog_asr_b200.air.AIRModel`` whose
+three hot-path operators are the oracle's torch restatements (``oracle/stn_ref_torch.py``,
+``oracle/asr_ref.py``) and plain reference ops for the composite (``air/air_number_bbox_location.py:722-727``).
+Used by tests/ (parity of the training step) and by bench.py's CPU-baseline leg; the product never imports it.
+Parity unpinned (see ``stn_ref_numpy.py``)."""
 import torch
 import torch.distributed as dist
 

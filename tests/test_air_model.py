@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 from mog_asr_b200 import synth
 from mog_asr_b200.air import AIRModel, Trainer, config_from_flags
-from tests.oracle_ops import OracleOps, SeededNoise
+from oracle.air_ops import OracleOps, SeededNoise
 
 
 def make_images(B, cs, seed=0):
