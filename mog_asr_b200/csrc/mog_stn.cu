@@ -40,6 +40,12 @@ int sm_count() {
     return cached[dev];
 }
 
+#ifndef MOG_FWD_GRID_PER_SM
+#define MOG_FWD_GRID_PER_SM (64 / MOG_WARPS_PER_CTA)
+#endif
+#ifndef MOG_BWD_GRID_PER_SM
+#define MOG_BWD_GRID_PER_SM (64 / MOG_WARPS_PER_CTA)
+#endif
 constexpr int kMaxSmemBytes = 200 * 1024;  // leave room under the 227 KB per-CTA limit
 
 // corner probe: same evaluation paths as the forward kernel (tables for separable thetas)
@@ -118,7 +124,7 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d too large for the per-warp row tables", a.g.Ho);
     if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
     const long long ctas = (a.B + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, 64 / kWarpsPerCta), kWarpThreads, smem, st>>>(a);
+    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, MOG_FWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
     MOG_CUDA_LAUNCH_CHECK("stn_fwd_warp_kernel");
     return MOG_OK;
 }
@@ -130,20 +136,19 @@ static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
                 a.g.Ho, a.g.Wo, a.g.Ws);
     if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC>, smem)) return rc;
     const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, 64 / kWarpsPerCta), kWarpThreads, smem, st>>>(a);
+    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, MOG_BWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
     MOG_CUDA_LAUNCH_CHECK("stn_bwd_warp_kernel");
     return MOG_OK;
 }
 
 template <bool COMPOSITE>
-static int launch_bwd(BwdArgs a, cudaStream_t st) {
+static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
+    // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
     const int nxc = (a.g.Ws + 31) / 32;
-    a.allow_sep = nxc <= 8 ? 1 : 0;  // wider sources use the general (atomic) path
     if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);
     if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st);
-    if (nxc <= 4) return launch_bwd_nxc<COMPOSITE, 4>(a, st);
-    return launch_bwd_nxc<COMPOSITE, 8>(a, st);
+    return launch_bwd_nxc<COMPOSITE, 4>(a, st);
 }
 
 }  // namespace mog

@@ -71,7 +71,6 @@ struct BwdArgs {
     float threshold;
     long long Bsrc;
     int u_div;
-    int allow_sep;  // 0: source too wide for the streaming path's register rows -> general path only
     Geo g;
 };
 
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
             const long long b = bs * a.u_div + t;
             Theta th;
             th.load(a.theta + 6 * b);
-            const bool sep = th.separable() && C == 1 && a.allow_sep;
+            const bool sep = th.separable() && C == 1;
             float z = 1.0f;
             bool active = true;
             if (COMPOSITE) {
@@ -468,11 +467,16 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                     }
                     rmax = __reduce_max_sync(0xffffffffu, rmax);
                     const int xa = s_col[jlo].x >> 2, xb = s_col[jhi].x >> 2;
-                    const int xlo = min(xa, xb);                 // footprint columns [xlo, xhi + 1]
-                    const int fw = max(xa, xb) + 2 - xlo;
-                    const int nxc = (fw + 31) >> 5;              // <= NXC
+                    const int fw = max(xa, xb) + 2 - min(xa, xb);   // footprint columns [xlo, xhi + 1]
                     const int njc = (jhi - jlo + 32) >> 5;
                     __syncwarp();
+                    // Source columns are handled in strips of NXC*32 (register budget): a footprint wider than
+                    // one strip streams the rows once per strip; dtheta/dz are accumulated in the first pass only.
+                    const int xlo_all = min(xa, xb), nxc_all = (fw + 31) >> 5;
+                    for (int cg = 0; cg < nxc_all && (cg == 0 || need_dU); cg += NXC) {
+                    const int xlo = xlo_all + cg * 32;
+                    const int nxc = min(NXC, nxc_all - cg);
+                    const bool first_pass = cg == 0;
                     int runA[NXC], runB[NXC];
 #pragma unroll
                     for (int c = 0; c < NXC; ++c) {
@@ -507,10 +511,14 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                                     const int i = ascending ? ilo + ii0 + rr : ihi - ii0 - rr;
                                     cy[r] = s_row[i];
                                     gq[r] = __ldg(gb + i * g.Wo + j);
-                                    const char* pa = Ubc + (unsigned)(cy[r].x + cj.x);
-                                    const char* pb = pa + ws4;
-                                    I[r][0] = ldg_f32(pa); I[r][2] = ldg_f32(pa + 4);
-                                    I[r][1] = ldg_f32(pb); I[r][3] = ldg_f32(pb + 4);
+                                    if (first_pass) {  // the taps only feed dtheta / dz
+                                        const char* pa = Ubc + (unsigned)(cy[r].x + cj.x);
+                                        const char* pb = pa + ws4;
+                                        I[r][0] = ldg_f32(pa); I[r][2] = ldg_f32(pa + 4);
+                                        I[r][1] = ldg_f32(pb); I[r][3] = ldg_f32(pb + 4);
+                                    } else {
+                                        I[r][0] = I[r][1] = I[r][2] = I[r][3] = 0.f;
+                                    }
                                 }
                             }
 #pragma unroll
@@ -592,6 +600,8 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                             }
                         }
                     }
+                    __syncwarp();
+                    }  // strips
                 }
                 // scale: dx_s = dx*(Ws-1.001)/2, dy_s = dy*(Hs-1.001)/2   (transformer.py:75-76)
                 p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
