@@ -4,7 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a kernels
     python bench.py --impl reference --steps K --warmup W    # the reference path's CPU restatement
 
-Workload (BASELINE.json configs[4]): per GPU B = 16384 canvases (canvas x canvas, C = 1),
+Workload (BASELINE.json configs[4]): the LARGEST cell of the config-5 sweep -- canvas 256x256,
+glimpse 64x64, prior-like theta (`--canvas/--glimpse/--regime` select any other cell, `--sweep` runs them
+all; the reference's own Multi-MNIST shapes are `--canvas 50 --glimpse 28`).  Per GPU B = 16384 canvases (C = 1),
 8 sequential AIR steps with a distinct theta per step; every step does what an AIR step asks of the
 sampler -- a *read* glimpse (canvas -> glimpse, theta_r) and a *write* glimpse (glimpse -> canvas,
 theta_w), each forward + backward(dU + dtheta).  One bench "step" = those 8 AIR steps over the batch
@@ -43,14 +45,15 @@ def parse_args():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--canvas", type=int, default=50)
-    p.add_argument("--glimpse", type=int, default=28)
+    p.add_argument("--canvas", type=int, default=256)
+    p.add_argument("--glimpse", type=int, default=64)
     p.add_argument("--batch", type=int, default=16384, help="canvases per GPU")
     p.add_argument("--regime", default="prior", choices=["prior", "full"])
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-train", action="store_true", help="skip the AIR-ASR training-step section")
-    p.add_argument("--cpu-sample", type=int, default=1024, help="canvases in the CPU-baseline sample")
+    p.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU-baseline sample (0 = sized for ~1 s per step)")
+    p.add_argument("--e2e-batch", type=int, default=0, help="canvases per GPU in the end-to-end leg (0 = at most 2 GB of pinned input)")
     p.add_argument("--sweep", action="store_true", help="run the whole config-5 sweep, write profiles/sweep_*.json")
     p.add_argument("--tag", default="", help="suffix for files written under profiles/")
     return p.parse_args()
@@ -284,7 +287,7 @@ def e2e_measure(a, dev, steps, warmup):
     import torch
     from mog_asr_b200 import synth
     from mog_asr_b200.host_api import HostSampler
-    B, cs, gs = a.batch, a.canvas, a.glimpse
+    B, cs, gs = a.e2e_batch, a.canvas, a.glimpse
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
     U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, gs, gs, 1), pin(B, cs, cs, 1)
     rng = np.random.default_rng(10)
@@ -318,7 +321,7 @@ def e2e_measure(a, dev, steps, warmup):
     fl = 4
     h2d = AIR_STEPS * fl * (U_h.numel() + g_r.numel() + W_h.numel() + g_w.numel() + 12 * B)
     d2h = AIR_STEPS * fl * (out_r.numel() + dU_r.numel() + out_w.numel() + dU_w.numel() + 12 * B)
-    chunks = -(-B // rd.chunk)
+    chunks = -(-B // rd.chunk)  # launches: 2 kernels per chunk per call
     return dt, h2d, d2h, AIR_STEPS * 2 * 2 * chunks
 
 
@@ -416,9 +419,10 @@ def run_ours(a):
         dt, h2d, d2h, e2e_launches = e2e_measure(a, dev, e_steps, 1)
         barrier()
         dt = max_over_ranks(dt)
-        e2e = dict(value=glimpses_per_step / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
-                   ms_per_step=dt * 1e3, steps=e_steps,
-                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams)")
+        e2e = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3, steps=e_steps, batch_per_gpu=a.e2e_batch,
+                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams); same cell and "
+                       "AIR steps on a slice of the batch (the leg is PCIe-bound, its rate does not depend on the batch)")
     tc2 = time.perf_counter()
     sampler.stop_flag = True
     clocks = sampler.summary(tc0, tc2 if e2e else tc1)
@@ -430,8 +434,9 @@ def run_ours(a):
         kernels = {k: dict(ms=kern_ms[k], share_of_step=kern_share[k], alg_bytes_per_launch=abytes[k],
                            achieved_gbs=abytes[k] / (kern_ms[k] * 1e-3) / 1e9,
                            frac=abytes[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds}
-        sym = dict(read_fwd="stn_fwd_kernel<false>", write_fwd="stn_fwd_kernel<false>",
-                   read_bwd="stn_bwd_kernel<false,true>", write_bwd="stn_bwd_kernel<false,true>")
+        nxc = lambda w: 1 if w <= 32 else (2 if w <= 64 else 4)
+        sym = dict(read_fwd="stn_fwd_warp_kernel<false>", write_fwd="stn_fwd_warp_kernel<false>",
+                   read_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.canvas)}>", write_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.glimpse)}>")
         roofline = dict(bound="hbm", kernel=f"{sym[dom]} ({dom})", achieved=kernels[dom]["achieved_gbs"], peak=peak,
                         unit="GB/s", frac=kernels[dom]["frac"], traffic=None, peak_source=peak_src,
                         step_alg_gbs=sum(abytes.values()) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9 * 1.0,
@@ -512,6 +517,11 @@ def run_sweep(a):
 
 def main():
     a = parse_args()
+    if a.cpu_sample <= 0:   # ~7e-8 s per output pixel and core for fwd+bwd of the C port -> about a second per step
+        px = AIR_STEPS * (a.glimpse ** 2 + 2 * a.canvas ** 2)
+        a.cpu_sample = int(max(64, min(1024, 2 ** round(np.log2(16 * 1.0 / (7e-8 * px))))))
+    if a.e2e_batch <= 0:
+        a.e2e_batch = int(max(256, min(a.batch, (2 << 30) // (4 * (2 * a.canvas ** 2 + 2 * a.glimpse ** 2)))))
     if a.impl == "reference":
         run_reference(a)
     elif a.sweep:
