@@ -437,8 +437,18 @@ def run_ours(a):
         nxc = lambda w: 1 if w <= 32 else (2 if w <= 64 else 4)
         sym = dict(read_fwd="stn_fwd_warp_kernel<false>", write_fwd="stn_fwd_warp_kernel<false>",
                    read_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.canvas)}>", write_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.glimpse)}>")
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this cell
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+            if tj["cell"] == dict(canvas=a.canvas, glimpse=a.glimpse, regime=a.regime, batch=a.batch):
+                traffic, traffic_src = tj["bytes_per_launch"][dom], tj["source"]
+        except Exception:
+            pass
         roofline = dict(bound="hbm", kernel=f"{sym[dom]} ({dom})", achieved=kernels[dom]["achieved_gbs"], peak=peak,
-                        unit="GB/s", frac=kernels[dom]["frac"], traffic=None, peak_source=peak_src,
+                        unit="GB/s", frac=kernels[dom]["frac"], traffic=traffic, traffic_source=traffic_src,
+                        algorithmic_bytes_per_launch=abytes[dom], peak_source=peak_src,
+                        note="write_bwd can exceed 1.0: the algorithmic count charges the whole canvas gradient (4*O), "
+                             "the kernel reads only the in-range rows/columns (the others cancel exactly)",
                         step_alg_gbs=sum(abytes.values()) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9 * 1.0,
                         kernels=kernels)
         roofline["step_frac"] = roofline["step_alg_gbs"] / peak

@@ -25,10 +25,12 @@ for r in rows[2:]:
     for i in idx:
         print(f"  {hdr[i]:<72} {r[i]:>16} {units[i]}")
     try:
-        rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")); wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", ""))
-        mult = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
-        t = float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"us": 1e-6, "ms": 1e-3, "ns": 1e-9}[units[hdr.index("gpu__time_duration.sum")]]
-        print(f"  {'traffic = dram read + write':<72} {(rd + wr) * mult / 1e6:>16.3f} MB  -> {(rd + wr) * mult / t / 1e9:.1f} GB/s")
+        U = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        rd = float(r[ir].replace(",", "")) * U[units[ir]]
+        wr = float(r[iw].replace(",", "")) * U[units[iw]]
+        t = float(r[it].replace(",", "")) * {"s": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9}[units[it]]
+        print(f"  {'traffic = dram read + write':<72} {(rd + wr) / 1e6:>16.3f} MB  -> {(rd + wr) / t / 1e9:.1f} GB/s")
     except Exception as e:
         print("  (traffic n/a)", e)
     s = sorted(((float(r[i].replace(",", "")) if r[i] else 0, hdr[i]) for i in stalls), reverse=True)[:6]
