@@ -40,6 +40,9 @@ int sm_count() {
     return cached[dev];
 }
 
+#ifndef MOG_COOP_ZERO_MIN_FLOATS
+#define MOG_COOP_ZERO_MIN_FLOATS 8192   // dU images of >= 32 KB are zero-filled by the whole CTA
+#endif
 #ifndef MOG_FWD_GRID_PER_SM
 #define MOG_FWD_GRID_PER_SM (64 / MOG_WARPS_PER_CTA)
 #endif
@@ -118,7 +121,7 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 template <bool COMPOSITE>
-static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+static int launch_fwd(FwdArgs a, cudaStream_t st) {
     if (a.B == 0) return MOG_OK;
     const size_t smem = (size_t)kWarpsPerCta * a.g.Ho * sizeof(int4);
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d too large for the per-warp row tables", a.g.Ho);
@@ -142,8 +145,9 @@ static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
 }
 
 template <bool COMPOSITE>
-static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
+    a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
     const int nxc = (a.g.Ws + 31) / 32;
     if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);

@@ -71,6 +71,7 @@ struct BwdArgs {
     float threshold;
     long long Bsrc;
     int u_div;
+    int coop_zero;  // 1: the CTA zero-fills its group's dU region in one linear sweep (large sources); 0: each warp its own
     Geo g;
 };
 
@@ -96,6 +97,21 @@ __device__ __forceinline__ T* opaque(T* p) {
     return p;
 }
 __device__ __forceinline__ float ldg_f32(const char* p) { return __ldg(reinterpret_cast<const float*>(p)); }
+
+// zero p[0, n) with the whole CTA: one linear, fully coalesced sweep (16-byte stores between the first and last
+// 16-byte boundaries).  Used for the contiguous dU / output region of the CTA's group of images: a few hundred
+// long linear streams chip-wide keep DRAM pages open, thousands of per-warp streams do not.
+__device__ __forceinline__ void fill_zero_cta(float* __restrict__ p, long long n) {
+    if (n <= 0) return;
+    const int mis = (int)((reinterpret_cast<uintptr_t>(p) >> 2) & 3);
+    const long long head = min(n, (long long)((4 - mis) & 3));
+    const long long nv = (n - head) >> 2;
+    const long long tail = head + 4 * nv;
+    if ((long long)threadIdx.x < head) p[threadIdx.x] = 0.0f;
+    float4* v = reinterpret_cast<float4*>(p + head);
+    for (long long k = threadIdx.x; k < nv; k += blockDim.x) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tail + threadIdx.x < n) p[tail + threadIdx.x] = 0.0f;
+}
 
 // zero p[begin, end) with 16-byte stores between the first and last 16-byte boundaries
 __device__ __forceinline__ void fill_zero(float* __restrict__ p, int begin, int end, int lane) {
@@ -172,19 +188,9 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kerne
     int4* s_row = s_dyn + warp * g.Ho;  // per-warp row table
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
 
-    const long long b_first = (long long)blockIdx.x * kWarpsPerCta + warp;
-#if MOG_FWD_PREFETCH
-    Theta th_next;
-    if (b_first < a.B) th_next.load(a.theta + 6 * b_first);
-#endif
-    for (long long b = b_first; b < a.B; b += nwarps) {
-#if MOG_FWD_PREFETCH
-        const Theta th = th_next;
-        if (b + nwarps < a.B) th_next.load(a.theta + 6 * (b + nwarps));  // prefetch: hides one DRAM latency per image
-#else
+    for (long long b = (long long)blockIdx.x * kWarpsPerCta + warp; b < a.B; b += nwarps) {
         Theta th;
         th.load(a.theta + 6 * b);
-#endif
         const bool sep = th.separable();
         float z = 1.0f;
         bool active = true;
@@ -394,10 +400,25 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
     const int SC = g.S * C;
     const float half_wsc = g.wsc * 0.5f, half_hsc = g.hsc * 0.5f;
 
-    for (long long bs = (long long)blockIdx.x * kWarpsPerCta + warp; bs < a.Bsrc; bs += nwarps) {
+    // One group of kWarpsPerCta consecutive source images per CTA iteration: the group's dU region is contiguous
+    // and is zero-filled by the whole CTA in one linear sweep; after the barrier every warp works on its own
+    // image (footprint rows overwrite the zeros while the lines are still in L2).
+    for (long long g0 = (long long)blockIdx.x * kWarpsPerCta; g0 < a.Bsrc; g0 += nwarps) {
+        if (a.dU && a.coop_zero) {
+            const long long ng = min((long long)kWarpsPerCta, a.Bsrc - g0);
+            __syncthreads();  // (uniform trip count: every warp of the CTA runs this loop the same number of times)
+            fill_zero_cta(a.dU + g0 * (long long)SC, ng * (long long)SC);
+            __syncthreads();
+        }
+        const long long bs = g0 + warp;
+        if (bs >= a.Bsrc) continue;
         const float* __restrict__ Ub = a.U + bs * (long long)SC;
         float* __restrict__ dUb = a.dU ? a.dU + bs * (long long)SC : nullptr;
-        bool dU_started = false;  // has this source image's dU been fully written once already?
+        if (dUb && !a.coop_zero) {   // small sources: the warp zero-fills its own image (no CTA barrier)
+            fill_zero(dUb, 0, SC, lane);
+            __syncwarp();
+        }
+        bool dU_started = true;  // zero-filled: every later write overwrites / accumulates rows the warp owns
 
         for (int t = 0; t < a.u_div; ++t) {
             const long long b = bs * a.u_div + t;
@@ -414,12 +435,12 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
             float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // dtheta (6) + dz
 
             if (!active) {
-                if (dUb && !dU_started) fill_zero(dUb, 0, SC, lane);
+                // (dU of an inactive image stays zero)
             } else if (!sep) {
                 // ---------- general affine / multi-channel: cold, out of line (writes dtheta/dz itself) ----
                 bwd_general_image<COMPOSITE>(Ub, dUb, gb, a.dtheta ? a.dtheta + 6 * b : nullptr,
                                              (COMPOSITE && a.dz) ? a.dz + b : nullptr, th.t[0], th.t[1], th.t[2], th.t[3],
-                                             th.t[4], th.t[5], z, !dU_started, lane, g.Hs, g.Ws, g.C, g.Ho, g.Wo, g.step_w,
+                                             th.t[4], th.t[5], z, false, lane, g.Hs, g.Ws, g.C, g.Ho, g.Wo, g.step_w,
                                              g.step_h, g.wsc, g.hsc);
                 dU_started = true;
                 continue;
@@ -431,8 +452,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                 // sit at base, base+4, base+Ws*4, base+Ws*4+4.
                 __syncwarp();
                 const bool need_dU = dUb != nullptr;
-                const bool first_write = !dU_started;
-                if (need_dU && first_write) fill_zero(dUb, 0, g.S, lane);  // footprint is overwritten below
+                const bool first_write = (t == 0);  // the group zero-fill made dU final outside the footprint
                 const int ws4 = g.Ws * 4;
                 int ilo = g.Ho, ihi = -1, jlo = g.Wo, jhi = -1;
                 for (int i = lane; i < g.Ho; i += 32) {
