@@ -325,6 +325,68 @@ def e2e_measure(a, dev, steps, warmup):
     return dt, h2d, d2h, AIR_STEPS * 2 * 2 * chunks
 
 
+def config1_section(dev, no_cpu):
+    """BASELINE configs[0]: glimpse read 50x50 -> 28x28, 3 steps, batch 64 (launch-bound: time, not roofline)."""
+    import torch
+    import mog_asr_b200 as M
+    from mog_asr_b200 import _lib, synth
+    L = _lib.load()
+    B, cs, gs, T = 64, 50, 28, 3
+    canv, _ = synth.multi_object_canvases(B, cs, 28, (1, 2, 3), seed=0)
+    U = torch.tensor(canv[..., None], device=dev)
+    ths = [torch.tensor(synth.theta_read(*synth.sxy_prior_like(B, seed=1 + t)), device=dev) for t in range(T)]
+    g = torch.randn((B, gs, gs, 1), device=dev)
+    out, dU, dth = torch.empty((B, gs, gs, 1), device=dev), torch.empty_like(U), torch.empty((B, 6), device=dev)
+    def step():
+        st = torch.cuda.current_stream(dev).cuda_stream   # (the capture below runs on its own stream)
+        for t in range(T):
+            _lib.check(L.mog_stn_forward(U.data_ptr(), ths[t].data_ptr(), out.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), "fwd")
+            _lib.check(L.mog_stn_backward(U.data_ptr(), ths[t].data_ptr(), g.data_ptr(), dU.data_ptr(), dth.data_ptr(),
+                                          B, cs, cs, 1, gs, gs, 1, st), "bwd")
+    for _ in range(20):
+        step()
+    reps = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    for _ in range(20):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    us_graph = e0.elapsed_time(e1) * 1e3 / reps
+    res = dict(workload="C1: read 50x50->28x28, 3 steps, batch 64, fwd+bwd(dU+dtheta), 6 launches",
+               gpu_us_eager=us, gpu_us_graph=us_graph, glimpses_per_sec_eager=B * T / (us * 1e-6),
+               glimpses_per_sec_graph=B * T / (us_graph * 1e-6))
+    if not no_cpu:
+        from oracle import stn_ref_c as RC
+        Un, gn = U.cpu().numpy(), g.cpu().numpy()
+        thn = [t.cpu().numpy() for t in ths]
+        for nthreads, key in ((1, "cpu_us_1thread"), (host_threads(), "cpu_us_all_threads")):
+            for _ in range(3):
+                RC.forward(Un, thn[0], (gs, gs), nthreads=nthreads)
+            t0 = time.perf_counter()
+            n = 20
+            for _ in range(n):
+                for t in range(T):
+                    RC.forward(Un, thn[t], (gs, gs), nthreads=nthreads)
+                    RC.backward(Un, thn[t], (gs, gs), gn, nthreads=nthreads)
+            res[key] = (time.perf_counter() - t0) / n * 1e6
+        res["cpu_cores"] = host_threads()
+    return res
+
+
 def train_section(a, dev, world, pg, rank):
     """Secondary metric of BASELINE.json: AIR-ASR training images/sec (configs 2-4) around the same kernels."""
     from mog_asr_b200.air import bench_train
@@ -465,6 +527,11 @@ def run_ours(a):
         if world == 1 and not a.no_cpu:
             cb, _ = cpu_measure(a, 3, 1, a.cpu_sample)
             line["cpu_baseline"] = cb
+        if world == 1:
+            try:
+                line["config1"] = config1_section(dev, a.no_cpu)
+            except Exception as e:
+                line["config1"] = dict(error=f"{type(e).__name__}: {e}")
     train = None
     if not a.no_train:
         try:

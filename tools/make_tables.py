@@ -8,9 +8,9 @@ sw = json.load(open(os.path.join(ROOT, "profiles", f"sweep_{tag}.json")))
 out = []
 k = b["roofline"]["kernels"]
 cb = b.get("cpu_baseline", {})
-out.append(f"### 3.1 Headline cell (config 5, canvas 50x50 <-> glimpse 28x28, prior-like theta, B = 16 384, 8 AIR steps) -- 1x B200\n")
+out.append(f"### 3.1 Headline cell -- 1x B200\n\n{b['config']['workload']}\n")
 out.append("| quantity | value |\n|---|---|")
-out.append(f"| glimpses/s, inputs resident (value) | {b['value']/1e6:.1f} M ({b['ms_per_step']:.2f} ms per 262 144 glimpses) |")
+out.append(f"| glimpses/s, inputs resident (value) | {b['value']/1e6:.1f} M ({b['ms_per_step']:.2f} ms per step of 262 144 glimpses) |")
 if "e2e" in b:
     out.append(f"| glimpses/s end to end, host buffers (e2e) | {b['e2e']['value']/1e6:.2f} M ({b['e2e']['h2d_bytes_per_step']/1e9:.2f} GB H2D + {b['e2e']['d2h_bytes_per_step']/1e9:.2f} GB D2H per step) |")
 if cb:
