@@ -24,9 +24,6 @@ namespace mog {
 #ifndef MOG_BWD_RB
 #define MOG_BWD_RB 4
 #endif
-#ifndef MOG_FWD_PREFETCH
-#define MOG_FWD_PREFETCH 0
-#endif
 #ifndef MOG_FWD_RB
 #define MOG_FWD_RB 8
 #endif
@@ -295,10 +292,6 @@ __host__ __device__ inline int bwd_warp_smem_words(const Geo& g) {
     return (4 * g.Ho + 4 * g.Wo + g.Ws + 2 * MOG_BWD_RB * (g.Wo + 1) + 3) & ~3;
 }
 
-template <int NXC>
-struct RowAcc {
-    float a0[NXC], a1[NXC];
-};
 
 // store (first transform: the image was zero-filled up front) or accumulate (later transforms of the same
 // source image) one dU element
@@ -418,7 +411,6 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
             fill_zero(dUb, 0, SC, lane);
             __syncwarp();
         }
-        bool dU_started = true;  // zero-filled: every later write overwrites / accumulates rows the warp owns
 
         for (int t = 0; t < a.u_div; ++t) {
             const long long b = bs * a.u_div + t;
@@ -442,7 +434,6 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                                              (COMPOSITE && a.dz) ? a.dz + b : nullptr, th.t[0], th.t[1], th.t[2], th.t[3],
                                              th.t[4], th.t[5], z, false, lane, g.Hs, g.Ws, g.C, g.Ho, g.Wo, g.step_w,
                                              g.step_h, g.wsc, g.hsc);
-                dU_started = true;
                 continue;
             } else {
                 // ---------- separable: gather form, streaming over rows ----------------------------------
@@ -627,7 +618,6 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                 p[0] *= half_wsc; p[1] *= half_wsc; p[2] *= half_wsc;
                 p[3] *= half_hsc; p[4] *= half_hsc; p[5] *= half_hsc;
             }
-            dU_started = true;
             // dtheta / dz: warp shuffle reduction
 #pragma unroll
             for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
