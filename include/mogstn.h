@@ -9,6 +9,7 @@
  *   mog_stn_corners            <- the clipped corner indices x0,x1,y0,y1   air/transformer.py:79-87 (parity probe)
  *   mog_stn_write_composite_*  <- write call site + canvas compositing     air/air_number_bbox_location.py:592-600,:718-727
  *   mog_asr_reg_*              <- ASR regularisers                         air/air_number_bbox_location.py:645-681,:970-1069
+ *   mog_bce_recon_*            <- reconstruction cross-entropy             air/air_number_bbox_location.py:945-968
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer to fp32 (or int32 where stated), dense row-major, owned by the
@@ -120,6 +121,15 @@ MOG_API int mog_asr_reg_backward(const float* log_odds, const float* shifts, con
                          float inv_global_batch, const float* g_per_image, const float* g_margin, int64_t B,
                          int T, const mog_asr_config* cfg, float* d_log_odds, float* d_shifts, float* d_scales,
                          void* stream);
+
+/* ---- reconstruction loss (the canvas epilogue right after the hot path) ------------------------------
+ * air/air_number_bbox_location.py:945-968: r = clip(canvas, 0, 1);
+ * loss[b] = -sum_p images*log(r + 1e-10) + (1 - images)*log(1 - r + 1e-10);  mse[b] = sum_p (images - r)^2 (nullable).
+ * canvas, images: [B][P].  Backward: dcanvas[b][p] = g_loss[b] * d loss[b] / d canvas[b][p] (fully overwritten). */
+MOG_API int mog_bce_recon_forward(const float* canvas, const float* images, float* loss, float* mse, int64_t B, int P,
+                          void* stream);
+MOG_API int mog_bce_recon_backward(const float* canvas, const float* images, const float* g_loss, float* dcanvas,
+                           int64_t B, int P, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@ as hand-written CUDA kernels behind the C ABI in ``include/mogstn.h``.  There is
 from .transformer import transformer, batch_transformer, stn_corners  # noqa: F401
 from .composite import write_composite  # noqa: F401
 from .asr import AsrRegulariser, asr_regularisers  # noqa: F401
+from .recon import reconstruction_loss  # noqa: F401
 
 __all__ = ["transformer", "batch_transformer", "stn_corners", "write_composite", "AsrRegulariser",
-           "asr_regularisers"]
+           "asr_regularisers", "reconstruction_loss"]

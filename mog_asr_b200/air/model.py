@@ -1,11 +1,12 @@
 """AIR-pPrior / AIR-ASR model (training graph) re-hosted in PyTorch.
 
 Follows ``/root/reference/air/air_number_bbox_location.py`` (``AIRModel._create_model``, ``:384-1122``) op for
-op; the three places where the reference touches the hot path go through an injectable ``ops`` object:
+op; the places where the reference touches the hot path (and the canvas epilogue that follows it) go through an injectable ``ops`` object:
 
   * read    ``:511-542``  ``ops.transformer(images[B,cs,cs,1], theta_r, (ws, ws))``
   * write + composite ``:563-600,:718-727``  ``ops.write_composite(canvas, vae_recon, theta_w, z_pres, stop_sum, thr)``
   * ASR regularisers ``:645-681,:970-1069``  ``ops.asr(cfg, log_odds[B,T], shifts[B,T,2], scales[B,T,1], ...)``
+  * reconstruction loss ``:945-968``  ``ops.recon_loss(images, canvas)`` (the epilogue right after the hot path)
 
 ``CudaOps`` (default) binds them to libmogstn's kernels.  The dense layers, LSTM cells and the elementwise
 KL / Concrete math stay in PyTorch (cuBLAS GEMMs; SURVEY 2.1 marks them out of scope as kernels).
@@ -84,6 +85,10 @@ class CudaOps:
     def write_composite(self, canvas, window, theta, z_pres, stop_sum, threshold):
         from ..composite import write_composite
         return write_composite(canvas, window, theta, z_pres, stop_sum, threshold)
+
+    def recon_loss(self, images, canvas):
+        from ..recon import reconstruction_loss
+        return reconstruction_loss(canvas, images)[0]
 
     def asr(self, cfg: AIRConfig, log_odds, shifts, scales):
         from ..asr import AsrRegulariser, asr_regularisers
@@ -268,11 +273,12 @@ class AIRModel(nn.Module):
 
         T = step
         elbo = sum(torch.stack(v, 1).sum(-1) for v in kl.values())                                          # :930-935
-        recon_c = torch.clamp(canvas.reshape(B, cs * cs), 0.0, 1.0)                                         # :947-948
+        canvas2 = canvas.reshape(B, cs * cs)
+        recon_c = torch.clamp(canvas2.detach(), 0.0, 1.0)                                                   # :947-948 (logged)
         if recon_loss_fn is None:
-            rec_loss = -(images * torch.log(recon_c + 1e-10) + (1.0 - images) * torch.log(1.0 - recon_c + 1e-10)).sum(1)  # :954-959
+            rec_loss = self.ops.recon_loss(images, canvas2)                                                 # :947-959 fused
         else:
-            rec_loss = recon_loss_fn(images, recon_c)
+            rec_loss = recon_loss_fn(images, torch.clamp(canvas2, 0.0, 1.0))
         elbo = elbo + rec_loss                                                                              # :968
         log_odds = torch.stack(lo_list, 1)
         shifts, scales = torch.stack(sh_list, 1), torch.stack(sc_list, 1)
@@ -284,4 +290,4 @@ class AIRModel(nn.Module):
         return dict(loss=loss, elbo=elbo.detach(), recon=rec_loss.detach(), steps=T, rec_num_digits=digits,
                     margin=margin.detach(), per_image_reg=per_image.detach(), components=comps,
                     rec_scales=scales.detach(), rec_shifts=shifts.detach(), z_pres_probs=torch.sigmoid(log_odds).detach(),
-                    reconstruction=recon_c.detach())
+                    reconstruction=recon_c)

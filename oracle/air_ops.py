@@ -21,6 +21,10 @@ class OracleOps:
         win = stn_ref_torch.transformer(window[..., None], theta, (cs, cs))[..., 0]
         return canvas + torch.where((stop_sum < threshold)[:, None, None], z_pres[:, None, None] * win, torch.zeros_like(win))
 
+    def recon_loss(self, images, canvas):
+        r = torch.clamp(canvas, 0.0, 1.0)                                   # air_number_bbox_location.py:947-948
+        return -(images * torch.log(r + 1e-10) + (1.0 - images) * torch.log(1.0 - r + 1e-10)).sum(1)   # :954-959
+
     def asr(self, cfg, log_odds, shifts, scales):
         pbar = None
         if cfg.constrains_margin_gamma > 1e-8:

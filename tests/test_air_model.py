@@ -110,9 +110,10 @@ def test_cuda_step_matches_oracle_step(cuda_device, flags):
     o_got = got.forward_backward(images, noise=SeededNoise(9, B, device=cuda_device))
     torch.cuda.synchronize()
     assert o_got["steps"] == o_ref["steps"]
-    # forward: the sampler and the composite are bit-exact, only the fp32 ASR kernel may differ in the last bits
+    # forward: the sampler and the composite are bit-exact; the fused cross-entropy and the ASR kernel are fp32
+    # sums in a different order
     assert torch.equal(o_got["reconstruction"], o_ref["reconstruction"])
-    assert torch.equal(o_got["elbo"], o_ref["elbo"])
+    assert torch.allclose(o_got["elbo"], o_ref["elbo"], rtol=2e-6, atol=1e-3)
     assert torch.equal(o_got["rec_num_digits"], o_ref["rec_num_digits"])
     np.testing.assert_allclose(o_got["per_image_reg"].cpu().numpy(), o_ref["per_image_reg"].cpu().numpy(), rtol=2e-4, atol=1e-3)
     np.testing.assert_allclose(float(o_got["loss"]), float(o_ref["loss"]), rtol=1e-5)
