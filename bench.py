@@ -135,7 +135,7 @@ def run_reference(a):
                 "here); its sampler restated in C (oracle/stn_ref.c), timed on the host cores on a bounded sample"),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -422,6 +422,14 @@ def train_cpu_baseline():
                 sample=f"{n} steps of config C2 (batch {gb}) with oracle/air_ops.py on torch-CPU")
 
 
+def trace(msg):
+    """progress marker on stderr (the JSON line is the only thing that goes to stdout)"""
+    print(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -450,7 +458,9 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    trace("building workload")
     wl = GpuWorkload(a, dev, seed=10 + rank)
+    trace("warm-up")
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(max(a.warmup, 3)):
@@ -466,6 +476,7 @@ def run_ours(a):
     barrier()
     tc1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    trace(f"timed region done: {ms_total / a.steps:.3f} ms/step")
     ms_per_step = ms_total / a.steps
     glimpses_per_step = a.batch * 2 * AIR_STEPS * world
     value = glimpses_per_step / (ms_per_step * 1e-3)
@@ -478,7 +489,9 @@ def run_ours(a):
     e2e_launches = 0
     if not a.no_e2e:
         e_steps = max(2, a.steps // 10)
+        trace("e2e leg")
         dt, h2d, d2h, e2e_launches = e2e_measure(a, dev, e_steps, 1)
+        trace("e2e done")
         barrier()
         dt = max_over_ranks(dt)
         e2e = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
@@ -534,14 +547,16 @@ def run_ours(a):
                 line["config1"] = dict(error=f"{type(e).__name__}: {e}")
     train = None
     if not a.no_train:
+        trace("train section")
         try:
             train = train_section(a, dev, world, dist.group.WORLD if world > 1 else None, rank)
         except Exception as e:  # never lose the headline line to the secondary metric
             train = dict(error=f"{type(e).__name__}: {e}")
+    trace("printing")
     if rank == 0:
         if train is not None:
             line["train"] = train
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -584,7 +599,7 @@ def run_sweep(a):
                                             frac=ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds})
                 row["step_frac"] = row["step_alg_gbs"] / peak
                 rows.append(row)
-                print(json.dumps(row), flush=True)
+                emit(row)
                 del wl
                 torch.cuda.empty_cache()
     out = os.path.join(ROOT, "profiles", f"sweep_{a.tag or 'latest'}.json")
@@ -592,8 +607,26 @@ def run_sweep(a):
         json.dump(dict(peak_gbs=peak, peak_source=peak_src, steps=a.steps, cells=rows), f, indent=1)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL: "NCCL version ..."), so fd 1 is
+    pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
     a = parse_args()
+    protect_stdout()
     if a.cpu_sample <= 0:   # ~7e-8 s per output pixel and core for fwd+bwd of the C port -> about a second per step
         px = AIR_STEPS * (a.glimpse ** 2 + 2 * a.canvas ** 2)
         a.cpu_sample = int(max(64, min(1024, 2 ** round(np.log2(16 * 1.0 / (7e-8 * px))))))
