@@ -224,3 +224,53 @@ def test_composite_equals_unfused_ops(cuda_device):
     win = M.transformer(U[..., None], th, (64, 64))[..., 0]
     unfused = canvas + torch.where((stop < 0.9)[:, None, None], z[:, None, None] * win, torch.zeros_like(win))
     assert torch.equal(fused, unfused)
+
+
+@pytest.mark.parametrize("canvas,glimpse,direction", [(50, 28, "write"), (256, 64, "read"), (256, 64, "write")])
+def test_full_size_properties_other_cells(cuda_device, canvas, glimpse, direction):
+    """BASELINE config-5 batch (16384) at the headline cell and in the write direction, through size-independent
+    properties: run-to-run determinism (forward and the gather-form backward), exact power-of-two linearity,
+    parity with the C oracle on a strided sample of the batch (forward bit-exact, gradients within GRAD_RTOL)."""
+    B = 16384
+    gen = torch.Generator(device=cuda_device).manual_seed(canvas + glimpse)
+    s, x, y = synth.sxy_prior_like(B, seed=3)
+    if direction == "read":
+        U = torch.rand((B, canvas, canvas, 1), device=cuda_device, generator=gen)
+        th, out_size = torch.tensor(synth.theta_read(s, x, y), device=cuda_device), (glimpse, glimpse)
+    else:
+        U = torch.rand((B, glimpse, glimpse, 1), device=cuda_device, generator=gen)
+        th, out_size = torch.tensor(synth.theta_write(s, x, y), device=cuda_device), (canvas, canvas)
+    go = torch.randn((B, out_size[0], out_size[1], 1), device=cuda_device, generator=gen)
+    Ug, tg = U.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    out = M.transformer(Ug, tg, out_size)
+    dU1, dt1 = torch.autograd.grad(out, (Ug, tg), go, retain_graph=True)
+    dU2, dt2 = torch.autograd.grad(out, (Ug, tg), go)
+    assert torch.equal(dU1, dU2) and torch.equal(dt1, dt2), "separable thetas: the backward is atomic-free and deterministic"
+    assert torch.equal(M.transformer(U * 0.5, th, out_size), out.detach() * 0.5)
+    idx = torch.arange(0, B, 1021, device=cuda_device)
+    Us, ts, gs_ = U[idx].cpu().numpy(), th[idx].cpu().numpy(), go[idx].cpu().numpy()
+    assert H.same_bits_or_nan(out.detach()[idx].cpu().numpy(), RC.forward(Us, ts, out_size))
+    dUs, dts = R.transformer_backward(Us, ts, out_size, gs_)
+    aU, ath = R.backward_term_magnitudes(Us, ts, out_size, gs_)
+    assert H.grad_excess(dU1[idx].cpu().numpy(), dUs, aU) <= 1.0
+    assert H.grad_excess(dt1[idx].cpu().numpy().reshape(-1, 2, 3), dts, ath) <= 1.0
+
+
+def test_host_buffer_entry_point_matches_device_path(cuda_device):
+    """mog_stn_fwd_bwd_host (the end-to-end leg of bench.py): pinned host arrays in/out, chunked over streams --
+    same bits as the device-resident calls, including a ragged last chunk and the dtheta-only form."""
+    from mog_asr_b200.host_api import HostSampler
+    rng = np.random.default_rng(77)
+    B = 1000                                    # chunk 256 -> three full chunks and a ragged one
+    U = torch.from_numpy(rng.random((B, 50, 50, 1), dtype=np.float32)).pin_memory()
+    s, x, y = synth.sxy_prior_like(B, seed=8)
+    th = torch.from_numpy(synth.theta_read(s, x, y)).pin_memory()
+    g = torch.from_numpy(rng.standard_normal((B, 28, 28, 1), dtype=np.float32)).pin_memory()
+    hs = HostSampler(cuda_device, (50, 50), (28, 28), 1, chunk=256, nstreams=3)
+    out, dU, dth = hs.fwd_bwd(U, th, g)
+    Ud, td = U.to(cuda_device).requires_grad_(True), th.to(cuda_device).requires_grad_(True)
+    o = M.transformer(Ud, td, (28, 28))
+    o.backward(g.to(cuda_device))
+    assert torch.equal(out, o.detach().cpu()) and torch.equal(dU, Ud.grad.cpu()) and torch.equal(dth, td.grad.cpu())
+    out2, dU2, dth2 = hs.fwd_bwd(U, th, g, need_dU=False)
+    assert dU2 is None and torch.equal(out2, out) and torch.equal(dth2, dth)
