@@ -113,13 +113,24 @@ class LSTMCellTF(nn.Module):
         self.bias = nn.Parameter(torch.zeros(4 * units))
         nn.init.xavier_uniform_(self.kernel)
 
-    def forward(self, x, state):
+    def forward(self, x, state, static_gates=None, static_width=0):
+        """``static_gates`` = ``x_static @ kernel[:static_width]`` for a leading block of the input that does not
+        change between steps (the flattened image, ``:416-419``): it is computed once per training step instead of
+        once per loop iteration -- the same sum, associated differently -- and ``x`` then holds only the rest."""
         c, h = state
-        gates = torch.addmm(self.bias, torch.cat([x, h], 1), self.kernel)
+        if static_gates is None:
+            gates = torch.addmm(self.bias, torch.cat([x, h], 1), self.kernel)
+        else:
+            gates = torch.addmm(static_gates, torch.cat([x, h], 1), self.kernel[static_width:])
         i, j, f, o = gates.chunk(4, 1)
         c2 = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
         h2 = torch.sigmoid(o) * torch.tanh(c2)
         return h2, (c2, h2)
+
+    def static_part(self, x_static):
+        """bias + x_static @ kernel[:width]  (one GEMM per training step for the image block)"""
+        w = x_static.shape[1]
+        return torch.addmm(self.bias, x_static, self.kernel[:w]), w
 
 
 def _dense(i, o):
@@ -214,6 +225,8 @@ class AIRModel(nn.Module):
         lo_list, sh_list, sc_list = [], [], []
         g_scale_lv = math.log(cfg.scale_prior_variance)
         images4 = images.reshape(B, cs, cs, 1)
+        # the image block of the inference LSTM input is the same at every step: its 2500x1024 GEMM runs once
+        img_gates, img_w = self.infer_cell.static_part(images)
 
         step = 0
         while step < cfg.max_steps:
@@ -223,7 +236,8 @@ class AIRModel(nn.Module):
                     flag = any_reduce(flag)
                 if not bool(flag):
                     break
-            out, inf_state = self.infer_cell(torch.cat([images, prev_latent, prev_ss], -1), inf_state)      # :413-422
+            out, inf_state = self.infer_cell(torch.cat([prev_latent, prev_ss], -1), inf_state,
+                                             static_gates=img_gates, static_width=img_w)                    # :413-422
             sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
             sh_var = torch.exp(sh_lv)
             shift_latent = sh_mean + noise("shift", step, (B, 2)) * torch.sqrt(sh_var)                      # :433-434
