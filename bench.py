@@ -387,6 +387,68 @@ def config1_section(dev, no_cpu):
     return res
 
 
+def aux_section(dev):
+    """The small kernels around the sampler: fused ASR regularisers (latency-bound: us per call, config 3 shape) and
+    the fused reconstruction loss (HBM-bound: GB/s over 8 B/pixel forward, 12 B/pixel backward)."""
+    import torch
+    import mog_asr_b200 as M
+    from mog_asr_b200.air import config_from_flags, CudaOps
+    peak, _ = peak_hbm()
+
+    def timeit(fn, reps):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) * 1e3 / reps   # us
+
+    out = {}
+    # ASR regularisers, config 3: B = 256, T = 6, -dn 3 -gb 1 -gs 10 -ga 20 (forward + backward, 2 launches)
+    cfg = config_from_flags("sprites", "3", ds="bbox20k", gb=1.0, gs=10.0, ga=20.0)
+    ops = CudaOps()
+    B, T = 256, 6
+    lo = torch.randn((B, T), device=dev, requires_grad=True)
+    sh = torch.tanh(torch.randn((B, T, 2), device=dev)).requires_grad_(True)
+    sc = torch.sigmoid(torch.randn((B, T, 1), device=dev) - 1).requires_grad_(True)
+
+    def asr():
+        per_image, margin, _ = ops.asr(cfg, lo, sh, sc)
+        (per_image.mean() + margin).backward()
+    out["asr_reg_fwd_bwd_us_B256_T6_eager"] = timeit(asr, 100)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        asr()
+    out["asr_reg_fwd_bwd_us_B256_T6_graph"] = timeit(g.replay, 200)
+    # same at a 16k batch with the count penalties on (3 launches: column sums, forward, backward)
+    cfg2 = config_from_flags("mnist", "13", gm=100.0, gne=10.0)
+    lo2 = torch.randn((16384, T), device=dev, requires_grad=True)
+    sh2 = torch.tanh(torch.randn((16384, T, 2), device=dev)).requires_grad_(True)
+    sc2 = torch.sigmoid(torch.randn((16384, T, 1), device=dev) - 1).requires_grad_(True)
+
+    def asr2():
+        per_image, margin, _ = ops.asr(cfg2, lo2, sh2, sc2)
+        (per_image.mean() + margin).backward()
+    out["asr_reg_fwd_bwd_us_B16384_T6_eager"] = timeit(asr2, 50)
+    # reconstruction loss at the headline canvas size
+    Bc, P = 16384, 256 * 256
+    canvas = (torch.rand((Bc, P), device=dev) * 1.2).requires_grad_(True)
+    images = torch.rand((Bc, P), device=dev)
+    gl = torch.rand(Bc, device=dev)
+    loss = M.reconstruction_loss(canvas, images)[0]
+    t_f = timeit(lambda: M.reconstruction_loss(canvas, images), 10)
+    t_b = timeit(lambda: torch.autograd.grad(loss, canvas, gl, retain_graph=True), 10)
+    out["bce_fwd"] = dict(us=t_f, gbs=8.0 * Bc * P / (t_f * 1e-6) / 1e9, frac=8.0 * Bc * P / (t_f * 1e-6) / 1e9 / peak,
+                          bytes_per_pixel=8, shape=[Bc, P])
+    out["bce_bwd"] = dict(us=t_b, gbs=12.0 * Bc * P / (t_b * 1e-6) / 1e9, frac=12.0 * Bc * P / (t_b * 1e-6) / 1e9 / peak,
+                          bytes_per_pixel=12, shape=[Bc, P])
+    return out
+
+
 def train_section(a, dev, world, pg, rank):
     """Secondary metric of BASELINE.json: AIR-ASR training images/sec (configs 2-4) around the same kernels."""
     from mog_asr_b200.air import bench_train
@@ -545,6 +607,12 @@ def run_ours(a):
                 line["config1"] = config1_section(dev, a.no_cpu)
             except Exception as e:
                 line["config1"] = dict(error=f"{type(e).__name__}: {e}")
+            try:
+                del wl
+                torch.cuda.empty_cache()
+                line["aux_kernels"] = aux_section(dev)
+            except Exception as e:
+                line["aux_kernels"] = dict(error=f"{type(e).__name__}: {e}")
     train = None
     if not a.no_train:
         trace("train section")

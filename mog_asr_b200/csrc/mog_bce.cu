@@ -51,16 +51,35 @@ __global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ 
     }
 }
 
+__device__ __forceinline__ float bce_dpx(float c, float x, float g) {
+    const float r = fmaxf(fminf(c, 1.0f), 0.0f);
+    const float d = -x / (r + kBceEps) + (1.0f - x) / (1.0f - r + kBceEps);
+    return (c >= 0.0f && c <= 1.0f) ? g * d : 0.0f;
+}
+
+// one CTA per image (grid-stride): g_loss[b] is loaded once, pixels stream through as float4
 __global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ canvas, const float* __restrict__ images,
                                                        const float* __restrict__ gloss, float* __restrict__ dcanvas,
                                                        long long B, int P) {
-    const long long n = B * (long long)P;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
-        const float c = __ldg(canvas + k), x = __ldg(images + k);
-        const float g = __ldg(gloss + k / P);
-        const float r = fmaxf(fminf(c, 1.0f), 0.0f);
-        const float d = -x / (r + kBceEps) + (1.0f - x) / (1.0f - r + kBceEps);
-        dcanvas[k] = (c >= 0.0f && c <= 1.0f) ? g * d : 0.0f;
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* c = canvas + b * P;
+        const float* x = images + b * P;
+        float* d = dcanvas + b * P;
+        const float g = __ldg(gloss + b);
+        const bool vec = ((reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(d)) & 15) == 0;
+        int done = 0;
+        if (vec) {
+            const int nv = P >> 2;
+            const float4* c4 = reinterpret_cast<const float4*>(c);
+            const float4* x4 = reinterpret_cast<const float4*>(x);
+            float4* d4 = reinterpret_cast<float4*>(d);
+            for (int k = threadIdx.x; k < nv; k += blockDim.x) {
+                const float4 cv = __ldg(c4 + k), xv = __ldg(x4 + k);
+                d4[k] = make_float4(bce_dpx(cv.x, xv.x, g), bce_dpx(cv.y, xv.y, g), bce_dpx(cv.z, xv.z, g), bce_dpx(cv.w, xv.w, g));
+            }
+            done = nv << 2;
+        }
+        for (int k = done + threadIdx.x; k < P; k += blockDim.x) d[k] = bce_dpx(__ldg(c + k), __ldg(x + k), g);
     }
 }
 
@@ -86,7 +105,7 @@ extern "C" int mog_bce_recon_backward(const float* canvas, const float* images, 
     MOG_REQUIRE(B >= 0 && P > 0, MOG_ERR_DIM, "bce backward: B=%lld P=%d", (long long)B, P);
     if (B == 0) return MOG_OK;
     MOG_REQUIRE(canvas && images && g_loss && dcanvas, MOG_ERR_NULL, "bce backward: NULL pointer");
-    long long blocks = (B * (long long)P + 255) / 256;
+    long long blocks = B;
     const long long cap = (long long)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     bce_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(canvas, images, g_loss, dcanvas, B, P);
