@@ -57,6 +57,8 @@ class AIRConfig:
     constrains_area_minmax: Sequence[float] = (17.0, 23.0)
     fix_steps: Optional[int] = None              # the count when -dn has one digit (train_air_pr.py:212)
     always_max_steps: bool = False               # run max_steps iterations regardless of the `any` test (:386-390)
+    stacked_kl: bool = True                      # evaluate the four KL terms once on [T,B,..] stacks after the loop
+                                                 # (same elementwise math as the per-step form, 6x fewer launches)
 
 
 def config_from_flags(data="mnist", dn="13", ds="", gn=0.0, gm=0.0, gne=0.0, gb=0.0, gs=0.0, ga=0.0, zt=0.1, **kw):
@@ -150,9 +152,11 @@ class _MeanVar(nn.Module):
         self.hv, self.v = _dense(in_dim + skip_dim, hidden), _dense(hidden + skip_dim, out_dim)
 
     def forward(self, x, skip=None):
-        cat = (lambda a: torch.cat([a, skip], -1)) if skip is not None else (lambda a: a)
-        mean = self.m(cat(F.relu(self.hm(cat(x)))))
-        logvar = self.v(cat(F.relu(self.hv(cat(x)))))
+        if skip is None:
+            return self.m(F.relu(self.hm(x))), self.v(F.relu(self.hv(x)))
+        xs = torch.cat([x, skip], -1)                       # shared by the mean and the log-variance branch
+        mean = self.m(torch.cat([F.relu(self.hm(xs)), skip], -1))
+        logvar = self.v(torch.cat([F.relu(self.hv(xs)), skip], -1))
         return mean, logvar
 
 
@@ -198,6 +202,17 @@ class AIRModel(nn.Module):
             return math.log(temp + eps) - y * (temp + 1) + lo - 2.0 * lse
         return logp(post_lo) - logp(prior_lo)
 
+    def _gaussian_kls(self, sc_mean, sc_lv, sh_mean, sh_lv, g_sh_mean, g_sh_lv, v_mean, v_lv):
+        """:731-736 (scale, fixed prior), :750-755 (shift, learned prior), :769-774 (VAE latent); last axis summed."""
+        cfg = self.cfg
+        scale_kl = 0.5 * (math.log(cfg.scale_prior_variance) - sc_lv - 1.0 + torch.exp(sc_lv) / cfg.scale_prior_variance
+                          + (sc_mean - cfg.scale_prior_mean) ** 2 / cfg.scale_prior_variance).sum(-1)
+        g_sh_var = torch.exp(g_sh_lv)
+        shift_kl = 0.5 * (g_sh_lv - sh_lv - 1.0 + torch.exp(sh_lv) / g_sh_var + (sh_mean - g_sh_mean) ** 2 / g_sh_var).sum(-1)
+        vae_kl = 0.5 * (math.log(cfg.vae_prior_variance) - v_lv - 1.0 + torch.exp(v_lv) / cfg.vae_prior_variance
+                        + (v_mean - cfg.vae_prior_mean) ** 2 / cfg.vae_prior_variance).sum(-1)
+        return scale_kl, shift_kl, vae_kl
+
     # ---- the training graph ----------------------------------------------------------------------------------
     def forward(self, images, noise: Optional[Callable] = None, any_reduce: Optional[Callable] = None,
                 global_batch: Optional[int] = None, recon_loss_fn: Optional[Callable] = None):
@@ -222,8 +237,8 @@ class AIRModel(nn.Module):
         canvas = z(B, cs, cs)
         digits = torch.zeros(B, dtype=torch.int32, device=dev)
         kl = {k: [] for k in ("z_pres_kl", "scale_kl", "shift_kl", "vae_kl")}
+        hist = {}
         lo_list, sh_list, sc_list = [], [], []
-        g_scale_lv = math.log(cfg.scale_prior_variance)
         images4 = images.reshape(B, cs, cs, 1)
         # the image block of the inference LSTM input is the same at every step: its 2500x1024 GEMM runs once
         img_gates, img_w = self.infer_cell.static_part(images)
@@ -236,8 +251,8 @@ class AIRModel(nn.Module):
                     flag = any_reduce(flag)
                 if not bool(flag):
                     break
-            out, inf_state = self.infer_cell(torch.cat([prev_latent, prev_ss], -1), inf_state,
-                                             static_gates=img_gates, static_width=img_w)                    # :413-422
+            prev = torch.cat([prev_latent, prev_ss], -1)   # input of both cells besides the image / the state
+            out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w)  # :413-422
             sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
             sh_var = torch.exp(sh_lv)
             shift_latent = sh_mean + noise("shift", step, (B, 2)) * torch.sqrt(sh_var)                      # :433-434
@@ -247,9 +262,8 @@ class AIRModel(nn.Module):
             scale_latent = sc_mean + noise("scale", step, (B, 1)) * torch.sqrt(sc_var)                      # :456-457
             inf_scale = torch.sigmoid(scale_latent)                                                         # :458
             ss_latent = torch.cat([shift_latent, scale_latent], -1)                                         # :463
-            gen_out, gen_state = self.gen_cell(torch.cat([prev_latent, prev_ss], -1), gen_state)            # :465-470
+            gen_out, gen_state = self.gen_cell(prev, gen_state)                                             # :465-470
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
-            g_sh_var = torch.exp(g_sh_lv)
 
             s, x, y = inf_scale[:, 0], inf_shift[:, 0], inf_shift[:, 1]
             zero = torch.zeros_like(s)
@@ -266,27 +280,39 @@ class AIRModel(nn.Module):
             u = noise("concrete", step, (B,))
             y_pre = (post_lo + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temp                  # concrete.py:20-27
             z_pres = torch.sigmoid(y_pre)                                                                   # :631
-            z_kl = self._concrete_kl(y_pre, prior_lo, post_lo, temp)                                        # :690-696
             active_prev = stop_sum < thr                                                                    # previous stop_sum (:698-702)
-            kl["z_pres_kl"].append(torch.where(active_prev, z_kl, torch.zeros_like(z_kl)))
             stop_sum = stop_sum + (1.0 - z_pres)                                                            # :712
             active = stop_sum < thr
             digits = digits + active.to(torch.int32)                                                        # :715-716
             canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
 
-            scale_kl = 0.5 * (g_scale_lv - sc_lv - 1.0 + sc_var / cfg.scale_prior_variance
-                              + (sc_mean - cfg.scale_prior_mean) ** 2 / cfg.scale_prior_variance).sum(-1)   # :731-736
-            shift_kl = 0.5 * (g_sh_lv - sh_lv - 1.0 + sh_var / g_sh_var + (sh_mean - g_sh_mean) ** 2 / g_sh_var).sum(-1)  # :750-755
-            vae_kl = 0.5 * (math.log(cfg.vae_prior_variance) - v_lv - 1.0 + torch.exp(v_lv) / cfg.vae_prior_variance
-                            + (v_mean - cfg.vae_prior_mean) ** 2 / cfg.vae_prior_variance).sum(1)           # :769-774
-            for k, v in (("scale_kl", scale_kl), ("shift_kl", shift_kl), ("vae_kl", vae_kl)):
-                kl[k].append(torch.where(active, v, torch.zeros_like(v)))                                   # masks use the NEW stop_sum
+            if cfg.stacked_kl:
+                # the KL terms are elementwise functions of per-step tensors: keep those, evaluate after the loop
+                for k, v in (("y_pre", y_pre), ("prior_lo", prior_lo), ("post_lo", post_lo), ("active_prev", active_prev),
+                             ("active", active), ("sc_mean", sc_mean), ("sc_lv", sc_lv), ("sh_mean", sh_mean), ("sh_lv", sh_lv),
+                             ("g_sh_mean", g_sh_mean), ("g_sh_lv", g_sh_lv), ("v_mean", v_mean), ("v_lv", v_lv)):
+                    hist.setdefault(k, []).append(v)
+            else:
+                z_kl = self._concrete_kl(y_pre, prior_lo, post_lo, temp)                                    # :690-696
+                kl["z_pres_kl"].append(torch.where(active_prev, z_kl, torch.zeros_like(z_kl)))
+                scale_kl, shift_kl, vae_kl = self._gaussian_kls(sc_mean, sc_lv, sh_mean, sh_lv, g_sh_mean, g_sh_lv, v_mean, v_lv)
+                for k, v in (("scale_kl", scale_kl), ("shift_kl", shift_kl), ("vae_kl", vae_kl)):
+                    kl[k].append(torch.where(active, v, torch.zeros_like(v)))                               # masks use the NEW stop_sum
             lo_list.append(post_lo); sh_list.append(inf_shift); sc_list.append(inf_scale)
             gen_prev_out, prev_latent, prev_ss = gen_out, v_latent, ss_latent
             step += 1
 
         T = step
-        elbo = sum(torch.stack(v, 1).sum(-1) for v in kl.values())                                          # :930-935
+        if cfg.stacked_kl:
+            H_ = {k: torch.stack(v, 0) for k, v in hist.items()}                                            # [T, B, ...]
+            z_kl = self._concrete_kl(H_["y_pre"], H_["prior_lo"], H_["post_lo"], temp)
+            scale_kl, shift_kl, vae_kl = self._gaussian_kls(H_["sc_mean"], H_["sc_lv"], H_["sh_mean"], H_["sh_lv"],
+                                                            H_["g_sh_mean"], H_["g_sh_lv"], H_["v_mean"], H_["v_lv"])
+            zero = torch.zeros_like(z_kl)
+            elbo = (torch.where(H_["active_prev"], z_kl, zero)
+                    + torch.where(H_["active"], scale_kl + shift_kl + vae_kl, zero)).sum(0)                 # :930-935
+        else:
+            elbo = sum(torch.stack(v, 1).sum(-1) for v in kl.values())                                      # :930-935
         canvas2 = canvas.reshape(B, cs * cs)
         recon_c = torch.clamp(canvas2.detach(), 0.0, 1.0)                                                   # :947-948 (logged)
         if recon_loss_fn is None:

@@ -53,6 +53,27 @@ def test_fix_steps_prior_and_always_max_steps():
     assert float(out["margin"]) == 0.0            # -gm unset: count penalties gated off (:973)
 
 
+@pytest.mark.parametrize("flags", [dict(data="mnist", dn="13", gm=100.0, gne=10.0),
+                                   dict(data="sprites", dn="3", ds="bbox20k", gb=1.0, gs=10.0, ga=20.0)])
+def test_stacked_kl_equals_per_step_form(flags):
+    """The fast form (KL terms evaluated once on [T,B,..] stacks after the loop) against the literal per-step form
+    of the reference (:690-787): same loss, same gradients (only the summation order over steps differs)."""
+    images, _ = make_images(6, 50 if flags["data"] == "mnist" else 64, seed=2)
+    res = []
+    for stacked in (False, True):
+        cfg = config_from_flags(stacked_kl=stacked, **flags)
+        tr = Trainer(cfg, "cpu", ops=OracleOps(), seed=5)
+        out = tr.forward_backward(images, noise=SeededNoise(4, 6))
+        res.append((float(out["loss"].detach()), out["elbo"].clone(), tr.flat_grad.clone(), out["steps"]))
+    (l0, e0, g0, t0), (l1, e1, g1, t1) = res
+    assert t0 == t1
+    np.testing.assert_allclose(l1, l0, rtol=1e-6)
+    assert torch.allclose(e1, e0, rtol=1e-5, atol=1e-4)
+    fin = torch.isfinite(g0)
+    assert torch.equal(torch.isfinite(g1), fin)
+    assert float((g1[fin] - g0[fin]).abs().max()) <= 1e-5 * float(g0[fin].abs().max())
+
+
 def _dp_worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -21,3 +21,10 @@ tot = sum(v[1] for v in agg.values()); n = sum(v[0] for v in agg.values())
 print(f"batch {B}: {n} kernels, {tot/1e3:.2f} ms of GPU time")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
     print(f"{c:5d} {t/1e3:8.3f} ms {100*t/tot:5.1f}%  {k}")
+ops = collections.Counter()
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CPU and e.name.startswith("aten::") and e.cpu_parent is not None and not e.cpu_parent.name.startswith("aten::"):
+        ops[e.name] += 1
+print("top-level aten ops:", sum(ops.values()))
+for k, c in ops.most_common(40):
+    print(f"{c:5d} {k}")
