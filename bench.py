@@ -53,7 +53,7 @@ def parse_args():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-train", action="store_true", help="skip the AIR-ASR training-step section")
     p.add_argument("--cpu-sample", type=int, default=0, help="canvases in the CPU-baseline sample (0 = sized for ~1 s per step)")
-    p.add_argument("--e2e-batch", type=int, default=0, help="canvases per GPU in the end-to-end leg (0 = at most 2 GB of pinned input)")
+    p.add_argument("--e2e-batch", type=int, default=0, help="canvases per GPU in the end-to-end leg (0 = the full batch)")
     p.add_argument("--sweep", action="store_true", help="run the whole config-5 sweep, write profiles/sweep_*.json")
     p.add_argument("--tag", default="", help="suffix for files written under profiles/")
     return p.parse_args()
@@ -290,11 +290,11 @@ def e2e_measure(a, dev, steps, warmup):
     B, cs, gs = a.e2e_batch, a.canvas, a.glimpse
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
     U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, gs, gs, 1), pin(B, cs, cs, 1)
-    rng = np.random.default_rng(10)
-    for t in (U_h, W_h):
-        t.copy_(torch.from_numpy(rng.random(tuple(t.shape), dtype=np.float32)))
-    for t in (g_r, g_w):
-        t.copy_(torch.from_numpy(rng.standard_normal(tuple(t.shape), dtype=np.float32)))
+    gdev = torch.Generator(device=dev).manual_seed(10)   # fill the host arrays from device-generated data (fast)
+    for t, normal in ((U_h, False), (W_h, False), (g_r, True), (g_w, True)):
+        tmp = (torch.randn if normal else torch.rand)(tuple(t.shape), device=dev, generator=gdev)
+        t.copy_(tmp)
+        del tmp
     gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
     th_r, th_w = [], []
     for t in range(AIR_STEPS):
@@ -550,7 +550,7 @@ def run_ours(a):
     e2e = None
     e2e_launches = 0
     if not a.no_e2e:
-        e_steps = max(2, a.steps // 10)
+        e_steps = 2 if a.batch * a.canvas ** 2 > (1 << 28) else max(2, a.steps // 10)
         trace("e2e leg")
         dt, h2d, d2h, e2e_launches = e2e_measure(a, dev, e_steps, 1)
         trace("e2e done")
@@ -558,8 +558,7 @@ def run_ours(a):
         dt = max_over_ranks(dt)
         e2e = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
                    d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3, steps=e_steps, batch_per_gpu=a.e2e_batch,
-                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams); same cell and "
-                       "AIR steps on a slice of the batch (the leg is PCIe-bound, its rate does not depend on the batch)")
+                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams)")
     tc2 = time.perf_counter()
     sampler.stop_flag = True
     clocks = sampler.summary(tc0, tc2 if e2e else tc1)
@@ -699,7 +698,10 @@ def main():
         px = AIR_STEPS * (a.glimpse ** 2 + 2 * a.canvas ** 2)
         a.cpu_sample = int(max(64, min(1024, 2 ** round(np.log2(16 * 1.0 / (7e-8 * px))))))
     if a.e2e_batch <= 0:
-        a.e2e_batch = int(max(256, min(a.batch, (2 << 30) // (4 * (2 * a.canvas ** 2 + 2 * a.glimpse ** 2)))))
+        # the full batch on one GPU; with N ranks on one host the pinned arrays (4 canvases' worth per image and rank)
+        # would not fit, so every rank takes batch/N images: the leg is host/PCIe-bound and its rate per byte is the same
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        a.e2e_batch = a.batch if world == 1 else max(2048, a.batch // world)
     if a.impl == "reference":
         run_reference(a)
     elif a.sweep:
