@@ -131,6 +131,28 @@ MOG_API int mog_bce_recon_forward(const float* canvas, const float* images, floa
 MOG_API int mog_bce_recon_backward(const float* canvas, const float* images, const float* g_loss, float* dcanvas,
                            int64_t B, int P, void* stream);
 
+/* ---- per-step elementwise math of the AIR loop body, fused ([B]-wide, latency-bound) ---------------
+ * gauss_sample: latent = mean + eps*sqrt(exp(logvar)); squashed = act(latent), act 0 none / 1 tanh / 2 sigmoid
+ *   (_sample_from_mvn :180-184 with :433-436, :456-459; air/vae.py:28-31).  n = number of elements.
+ *   backward: g_latent / g_squashed nullable; d_mean, d_logvar fully overwritten.
+ * thetas: shift[B][2], scale[B] -> theta_r = [[s,0,x],[0,s,y]] (:511-531), theta_w = [[1/s,0,-x/s],[0,1/s,-y/s]] (:563-584).
+ * zpres: Concrete sample (air/concrete.py:20-27), z_pres = sigmoid(y) (:631), stop_out = stop_in + 1 - z_pres (:712),
+ *   active_prev / active = stop < threshold before / after the update (1 byte each). */
+MOG_API int mog_air_gauss_sample_forward(const float* mean, const float* logvar, const float* eps, float* latent,
+                                 float* squashed, int64_t n, int act, void* stream);
+MOG_API int mog_air_gauss_sample_backward(const float* logvar, const float* eps, const float* squashed, const float* g_latent,
+                                  const float* g_squashed, float* d_mean, float* d_logvar, int64_t n, int act,
+                                  void* stream);
+MOG_API int mog_air_thetas_forward(const float* shift, const float* scale, float* theta_r, float* theta_w, int64_t B,
+                           void* stream);
+MOG_API int mog_air_thetas_backward(const float* shift, const float* scale, const float* g_theta_r, const float* g_theta_w,
+                            float* d_shift, float* d_scale, int64_t B, void* stream);
+MOG_API int mog_air_zpres_forward(const float* log_odds, const float* u, const float* stop_in, float temperature,
+                          float threshold, float* y_pre, float* z_pres, float* stop_out, unsigned char* active_prev,
+                          unsigned char* active, int64_t B, void* stream);
+MOG_API int mog_air_zpres_backward(const float* z_pres, const float* g_y, const float* g_z, float temperature,
+                           float* d_log_odds, int64_t B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

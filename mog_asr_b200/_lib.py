@@ -40,6 +40,12 @@ SIGNATURES = {
     "mog_stn_write_composite_backward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
     "mog_bce_recon_forward": [_vp, _vp, _vp, _vp, _i64, _int, _vp],
     "mog_bce_recon_backward": [_vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_gauss_sample_forward": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_gauss_sample_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_thetas_forward": [_vp, _vp, _vp, _vp, _i64, _vp],
+    "mog_air_thetas_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "mog_air_zpres_forward": [_vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "mog_air_zpres_backward": [_vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "mog_asr_reg_colsum": [_vp, _vp, _i64, _int, _vp],
     "mog_asr_reg_forward": [_vp, _vp, _vp, _vp, _f32, _i64, _int, ctypes.POINTER(AsrConfig), _vp, _vp, _vp, _vp],
     "mog_asr_reg_backward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _int, ctypes.POINTER(AsrConfig), _vp, _vp, _vp, _vp],

@@ -1,0 +1,123 @@
+"""Fused per-step elementwise math of the AIR loop body (csrc/mog_air.cu): each call is one
+kernel forward and one backward instead of ~10 / ~20 framework ops.  See include/mogstn.h for the formulas and the
+reference lines they replace."""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from ..transformer import _need_cuda, _stream
+
+_ACT = {None: 0, "none": 0, "tanh": 1, "sigmoid": 2}
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+class _GaussSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, logvar, eps, act):
+        L = _lib.load()
+        latent = torch.empty_like(mean)
+        squashed = torch.empty_like(mean) if act else None
+        with torch.cuda.device(mean.device):
+            _lib.check(L.mog_air_gauss_sample_forward(_p(mean), _p(logvar), _p(eps), _p(latent), _p(squashed), mean.numel(),
+                                                      act, _stream(mean)), "mog_air_gauss_sample_forward")
+        ctx.save_for_backward(logvar, eps, squashed)
+        ctx.act = act
+        return (latent, squashed) if act else (latent, latent.new_empty(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_latent, g_squashed):
+        logvar, eps, squashed = ctx.saved_tensors
+        L = _lib.load()
+        g_latent = g_latent.contiguous() if g_latent is not None else None
+        g_squashed = g_squashed.contiguous() if (ctx.act and g_squashed is not None) else None
+        d_mean, d_logvar = torch.empty_like(logvar), torch.empty_like(logvar)
+        with torch.cuda.device(logvar.device):
+            _lib.check(L.mog_air_gauss_sample_backward(_p(logvar), _p(eps), _p(squashed), _p(g_latent), _p(g_squashed),
+                                                       _p(d_mean), _p(d_logvar), logvar.numel(), ctx.act, _stream(logvar)),
+                       "mog_air_gauss_sample_backward")
+        return d_mean, d_logvar, None, None
+
+
+def gauss_sample(mean, logvar, eps, act=None):
+    """``latent = mean + eps*sqrt(exp(logvar))`` and ``act(latent)`` (``act`` in None/'tanh'/'sigmoid').
+    Returns ``(latent, squashed)``; ``squashed`` is None when ``act`` is None."""
+    for t, n in ((mean, "mean"), (logvar, "logvar"), (eps, "eps")):
+        _need_cuda(t, n)
+    a = _ACT[act]
+    latent, squashed = _GaussSample.apply(mean.float().contiguous(), logvar.float().contiguous(), eps.float().contiguous(), a)
+    return latent, (squashed if a else None)
+
+
+class _Thetas(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shift, scale):
+        L = _lib.load()
+        B = shift.shape[0]
+        th_r = torch.empty((B, 6), dtype=torch.float32, device=shift.device)
+        th_w = torch.empty((B, 6), dtype=torch.float32, device=shift.device)
+        with torch.cuda.device(shift.device):
+            _lib.check(L.mog_air_thetas_forward(_p(shift), _p(scale), _p(th_r), _p(th_w), B, _stream(shift)), "mog_air_thetas_forward")
+        ctx.save_for_backward(shift, scale)
+        return th_r, th_w
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_r, g_w):
+        shift, scale = ctx.saved_tensors
+        L = _lib.load()
+        B = shift.shape[0]
+        d_shift, d_scale = torch.empty_like(shift), torch.empty_like(scale)
+        with torch.cuda.device(shift.device):
+            _lib.check(L.mog_air_thetas_backward(_p(shift), _p(scale), _p(g_r.contiguous()), _p(g_w.contiguous()), _p(d_shift),
+                                                 _p(d_scale), B, _stream(shift)), "mog_air_thetas_backward")
+        return d_shift, d_scale
+
+
+def thetas(inf_shift, inf_scale):
+    """``inf_shift [B,2]`` (tanh of the shift latent), ``inf_scale [B,1]`` -> ``(theta_read [B,6], theta_write [B,6])``."""
+    _need_cuda(inf_shift, "inf_shift")
+    _need_cuda(inf_scale, "inf_scale")
+    return _Thetas.apply(inf_shift.float().contiguous(), inf_scale.float().reshape(-1).contiguous())
+
+
+class _ZPres(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, log_odds, u, stop_sum, temperature, threshold):
+        L = _lib.load()
+        B = log_odds.shape[0]
+        dev = log_odds.device
+        y, z, s1 = torch.empty_like(log_odds), torch.empty_like(log_odds), torch.empty_like(log_odds)
+        ap = torch.empty(B, dtype=torch.bool, device=dev)
+        ac = torch.empty(B, dtype=torch.bool, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.mog_air_zpres_forward(_p(log_odds), _p(u), _p(stop_sum), float(temperature), float(threshold), _p(y), _p(z),
+                                               _p(s1), _p(ap), _p(ac), B, _stream(log_odds)), "mog_air_zpres_forward")
+        ctx.save_for_backward(z)
+        ctx.temperature = float(temperature)
+        ctx.mark_non_differentiable(s1, ap, ac)
+        return y, z, s1, ap, ac
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_y, g_z, _gs, _gap, _gac):
+        (z,) = ctx.saved_tensors
+        L = _lib.load()
+        d_lo = torch.empty_like(z)
+        g_y = g_y.contiguous() if g_y is not None else None
+        g_z = g_z.contiguous() if g_z is not None else None
+        with torch.cuda.device(z.device):
+            _lib.check(L.mog_air_zpres_backward(_p(z), _p(g_y), _p(g_z), ctx.temperature, _p(d_lo), z.shape[0], _stream(z)),
+                       "mog_air_zpres_backward")
+        return d_lo, None, None, None, None
+
+
+def zpres(log_odds, u, stop_sum, temperature, threshold):
+    """Concrete sample + stopping-sum update: returns ``(y_pre, z_pres, stop_sum_new, active_prev, active)``."""
+    for t, n in ((log_odds, "log_odds"), (u, "u"), (stop_sum, "stop_sum")):
+        _need_cuda(t, n)
+    return _ZPres.apply(log_odds.float().contiguous(), u.float().contiguous(), stop_sum.detach().float().contiguous(), temperature, threshold)

@@ -75,10 +75,12 @@ def config_from_flags(data="mnist", dn="13", ds="", gn=0.0, gm=0.0, gne=0.0, gb=
 
 
 class CudaOps:
-    """The hot-path operators bound to libmogstn (the product path)."""
+    """The hot-path operators bound to libmogstn (the product path).  ``fused_pointwise=False`` keeps the per-step
+    elementwise math (sampling, theta construction, z_pres) in framework ops, written like the reference -- the
+    kernels are still the sampler / composite / regulariser / loss ones; used to check the fused forms."""
 
-    def __init__(self, process_group=None, global_batch=None):
-        self.process_group, self.global_batch = process_group, global_batch
+    def __init__(self, process_group=None, global_batch=None, fused_pointwise=True):
+        self.process_group, self.global_batch, self.fused_pointwise = process_group, global_batch, fused_pointwise
 
     def transformer(self, U, theta, out_size):
         from ..transformer import transformer
@@ -91,6 +93,32 @@ class CudaOps:
     def recon_loss(self, images, canvas):
         from ..recon import reconstruction_loss
         return reconstruction_loss(canvas, images)[0]
+
+    # per-step elementwise math (csrc/mog_air.cu)
+    def gauss_sample(self, mean, logvar, eps, act=None):
+        if self.fused_pointwise:
+            from .fused import gauss_sample
+            return gauss_sample(mean, logvar, eps, act)
+        latent = mean + eps * torch.sqrt(torch.exp(logvar))                                   # :180-184
+        return latent, (torch.tanh(latent) if act == "tanh" else torch.sigmoid(latent) if act == "sigmoid" else None)
+
+    def thetas(self, inf_shift, inf_scale):
+        if self.fused_pointwise:
+            from .fused import thetas
+            return thetas(inf_shift, inf_scale)
+        s, x, y = inf_scale[:, 0], inf_shift[:, 0], inf_shift[:, 1]
+        zero = torch.zeros_like(s)
+        return (torch.stack([s, zero, x, zero, s, y], 1),                                     # :511-531
+                torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1))               # :563-584
+
+    def zpres(self, log_odds, u, stop_sum, temperature, threshold):
+        if self.fused_pointwise:
+            from .fused import zpres
+            return zpres(log_odds, u, stop_sum, temperature, threshold)
+        y_pre = (log_odds + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temperature   # concrete.py:20-27
+        z_pres = torch.sigmoid(y_pre)                                                         # :631
+        stop_new = stop_sum + (1.0 - z_pres)                                                  # :712
+        return y_pre, z_pres, stop_new, stop_sum < threshold, stop_new < threshold
 
     def asr(self, cfg: AIRConfig, log_odds, shifts, scales):
         from ..asr import AsrRegulariser, asr_regularisers
@@ -188,7 +216,7 @@ class AIRModel(nn.Module):
         for l in self.vae_rec:
             x = F.softplus(l(x))
         mean, logvar = self.vae_rec_mean(x), self.vae_rec_logvar(x)
-        latent = mean + eps * torch.sqrt(torch.exp(logvar))
+        latent, _ = self.ops.gauss_sample(mean, logvar, eps)                 # vae.py:28-31
         x = latent
         for l in self.vae_gen:
             x = F.softplus(l(x))
@@ -254,35 +282,24 @@ class AIRModel(nn.Module):
             prev = torch.cat([prev_latent, prev_ss], -1)   # input of both cells besides the image / the state
             out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w)  # :413-422
             sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
-            sh_var = torch.exp(sh_lv)
-            shift_latent = sh_mean + noise("shift", step, (B, 2)) * torch.sqrt(sh_var)                      # :433-434
-            inf_shift = torch.tanh(shift_latent)                                                            # :435
+            shift_latent, inf_shift = self.ops.gauss_sample(sh_mean, sh_lv, noise("shift", step, (B, 2)), "tanh")    # :433-435
             sc_mean, sc_lv = self.inf_scale(out, shift_latent)                                              # :439-455
-            sc_var = torch.exp(sc_lv)
-            scale_latent = sc_mean + noise("scale", step, (B, 1)) * torch.sqrt(sc_var)                      # :456-457
-            inf_scale = torch.sigmoid(scale_latent)                                                         # :458
+            scale_latent, inf_scale = self.ops.gauss_sample(sc_mean, sc_lv, noise("scale", step, (B, 1)), "sigmoid")  # :456-458
             ss_latent = torch.cat([shift_latent, scale_latent], -1)                                         # :463
             gen_out, gen_state = self.gen_cell(prev, gen_state)                                             # :465-470
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
 
-            s, x, y = inf_scale[:, 0], inf_shift[:, 0], inf_shift[:, 1]
-            zero = torch.zeros_like(s)
-            theta_r = torch.stack([s, zero, x, zero, s, y], 1)                                              # :511-531
+            theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)                                        # :511-531,:563-584
             window = self.ops.transformer(images4, theta_r, (ws, ws))[:, :, :, 0]                           # :534-542
             recon, v_mean, v_lv, v_latent = self._vae(window.reshape(B, ws * ws), noise("vae", step, (B, L)))  # :544-553
-            theta_w = torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1)                        # :563-584
 
             if cfg.fix_steps is not None:                                                                   # :604-608
                 prior_lo = torch.full((B,), 100.0 if step < cfg.fix_steps else -100.0, device=dev, dtype=dt)
             else:
                 prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev_out)))[:, 0]                         # :609-615
             post_lo = self.z_post(F.relu(self.z_post_h(out)))[:, 0]                                         # :620-623
-            u = noise("concrete", step, (B,))
-            y_pre = (post_lo + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temp                  # concrete.py:20-27
-            z_pres = torch.sigmoid(y_pre)                                                                   # :631
-            active_prev = stop_sum < thr                                                                    # previous stop_sum (:698-702)
-            stop_sum = stop_sum + (1.0 - z_pres)                                                            # :712
-            active = stop_sum < thr
+            y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
+                                                                          temp, thr)     # concrete.py:20-27, :631, :698-712
             digits = digits + active.to(torch.int32)                                                        # :715-716
             canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
 

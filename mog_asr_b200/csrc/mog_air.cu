@@ -1,0 +1,164 @@
+// libmogstn -- per-step elementwise math of the AIR loop body, fused.
+//
+// /root/reference/air/air_number_bbox_location.py builds these from ~10 TF ops each, every loop iteration:
+//   gauss_sample : _sample_from_mvn (:180-184) + tanh/sigmoid squashing of the shift / scale latents (:433-436,
+//                  :456-459) and the VAE latent draw (air/vae.py:28-31):  latent = mean + eps*sqrt(exp(logvar))
+//   thetas       : theta_r = [[s,0,x],[0,s,y]] (:511-531), theta_w = [[1/s,0,-x/s],[0,1/s,-y/s]] (:563-584)
+//   zpres        : Concrete sample y = (log_odds + log(u+eps) - log(1-u+eps))/temperature (air/concrete.py:20-27),
+//                  z_pres = sigmoid(y) (:631), stopping_sum += 1 - z_pres (:712), the two activity masks
+//                  (stopping_sum < threshold before / after the update, :698-702 / :722-787)
+// One launch forward and one backward each; [B]-wide, latency-bound (no roofline claim).
+#include "mog_common.cuh"
+
+namespace mog {
+
+constexpr int kAirThreads = 256;
+static inline int air_blocks(long long n) {
+    long long b = (n + kAirThreads - 1) / kAirThreads;
+    const long long cap = (long long)sm_count() * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// act: 0 = none, 1 = tanh, 2 = sigmoid
+__global__ void air_gauss_fwd(const float* __restrict__ mean, const float* __restrict__ logvar, const float* __restrict__ eps,
+                              float* __restrict__ latent, float* __restrict__ squashed, long long n, int act) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const float l = mean[k] + eps[k] * sqrtf(expf(logvar[k]));
+        latent[k] = l;
+        if (act == 1) squashed[k] = tanhf(l);
+        else if (act == 2) squashed[k] = 1.0f / (1.0f + expf(-l));
+    }
+}
+
+// g_latent / g_squashed nullable; squashed = saved forward output (act != 0)
+__global__ void air_gauss_bwd(const float* __restrict__ logvar, const float* __restrict__ eps, const float* __restrict__ squashed,
+                              const float* __restrict__ g_latent, const float* __restrict__ g_squashed,
+                              float* __restrict__ d_mean, float* __restrict__ d_logvar, long long n, int act) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        float dl = g_latent ? g_latent[k] : 0.0f;
+        if (act != 0 && g_squashed) {
+            const float a = squashed[k];
+            dl += g_squashed[k] * (act == 1 ? (1.0f - a * a) : a * (1.0f - a));
+        }
+        d_mean[k] = dl;
+        d_logvar[k] = dl * eps[k] * 0.5f * sqrtf(expf(logvar[k]));
+    }
+}
+
+__global__ void air_thetas_fwd(const float* __restrict__ shift, const float* __restrict__ scale, float* __restrict__ theta_r,
+                               float* __restrict__ theta_w, long long B) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const float s = scale[b], x = shift[2 * b], y = shift[2 * b + 1];
+        float* r = theta_r + 6 * b;
+        r[0] = s; r[1] = 0.0f; r[2] = x; r[3] = 0.0f; r[4] = s; r[5] = y;
+        float* w = theta_w + 6 * b;
+        const float inv = 1.0f / s;          // fp32 divides like the reference graph (:570-578)
+        w[0] = inv; w[1] = 0.0f; w[2] = -x / s; w[3] = 0.0f; w[4] = inv; w[5] = -y / s;
+    }
+}
+
+__global__ void air_thetas_bwd(const float* __restrict__ shift, const float* __restrict__ scale, const float* __restrict__ g_r,
+                               const float* __restrict__ g_w, float* __restrict__ d_shift, float* __restrict__ d_scale, long long B) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const float s = scale[b], x = shift[2 * b], y = shift[2 * b + 1];
+        const float* r = g_r + 6 * b;
+        const float* w = g_w + 6 * b;
+        const float inv = 1.0f / s, inv2 = inv * inv;
+        d_scale[b] = (r[0] + r[4]) - (w[0] + w[4]) * inv2 + (x * w[2] + y * w[5]) * inv2;
+        d_shift[2 * b] = r[2] - w[2] * inv;
+        d_shift[2 * b + 1] = r[5] - w[5] * inv;
+    }
+}
+
+__global__ void air_zpres_fwd(const float* __restrict__ log_odds, const float* __restrict__ u, const float* __restrict__ stop_in,
+                              float temperature, float threshold, float* __restrict__ y_pre, float* __restrict__ z_pres,
+                              float* __restrict__ stop_out, unsigned char* __restrict__ active_prev,
+                              unsigned char* __restrict__ active, long long B) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const float uu = u[b];
+        const float y = (log_odds[b] + logf(uu + 10e-10f) - logf(1.0f - uu + 10e-10f)) / temperature;
+        const float z = 1.0f / (1.0f + expf(-y));
+        const float s0 = stop_in[b], s1 = s0 + (1.0f - z);
+        y_pre[b] = y; z_pres[b] = z; stop_out[b] = s1;
+        active_prev[b] = s0 < threshold; active[b] = s1 < threshold;
+    }
+}
+
+__global__ void air_zpres_bwd(const float* __restrict__ z_pres, const float* __restrict__ g_y, const float* __restrict__ g_z,
+                              float temperature, float* __restrict__ d_log_odds, long long B) {
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+        const float z = z_pres[b];
+        const float dy = (g_y ? g_y[b] : 0.0f) + (g_z ? g_z[b] * z * (1.0f - z) : 0.0f);
+        d_log_odds[b] = dy / temperature;
+    }
+}
+
+}  // namespace mog
+
+using namespace mog;
+
+extern "C" int mog_air_gauss_sample_forward(const float* mean, const float* logvar, const float* eps, float* latent,
+                                            float* squashed, int64_t n, int act, void* stream) {
+    MOG_REQUIRE(n >= 0 && act >= 0 && act <= 2, MOG_ERR_DIM, "gauss_sample: n=%lld act=%d", (long long)n, act);
+    if (n == 0) return MOG_OK;
+    MOG_REQUIRE(mean && logvar && eps && latent && (act == 0 || squashed), MOG_ERR_NULL, "gauss_sample forward: NULL pointer");
+    air_gauss_fwd<<<air_blocks(n), kAirThreads, 0, (cudaStream_t)stream>>>(mean, logvar, eps, latent, squashed, n, act);
+    MOG_CUDA_LAUNCH_CHECK("air_gauss_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_gauss_sample_backward(const float* logvar, const float* eps, const float* squashed, const float* g_latent,
+                                             const float* g_squashed, float* d_mean, float* d_logvar, int64_t n, int act,
+                                             void* stream) {
+    MOG_REQUIRE(n >= 0 && act >= 0 && act <= 2, MOG_ERR_DIM, "gauss_sample: n=%lld act=%d", (long long)n, act);
+    if (n == 0) return MOG_OK;
+    MOG_REQUIRE(logvar && eps && d_mean && d_logvar && (act == 0 || !g_squashed || squashed), MOG_ERR_NULL,
+                "gauss_sample backward: NULL pointer");
+    air_gauss_bwd<<<air_blocks(n), kAirThreads, 0, (cudaStream_t)stream>>>(logvar, eps, squashed, g_latent, g_squashed, d_mean,
+                                                                         d_logvar, n, act);
+    MOG_CUDA_LAUNCH_CHECK("air_gauss_bwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_thetas_forward(const float* shift, const float* scale, float* theta_r, float* theta_w, int64_t B,
+                                      void* stream) {
+    MOG_REQUIRE(B >= 0, MOG_ERR_DIM, "thetas: B=%lld", (long long)B);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(shift && scale && theta_r && theta_w, MOG_ERR_NULL, "thetas forward: NULL pointer");
+    air_thetas_fwd<<<air_blocks(B), kAirThreads, 0, (cudaStream_t)stream>>>(shift, scale, theta_r, theta_w, B);
+    MOG_CUDA_LAUNCH_CHECK("air_thetas_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_thetas_backward(const float* shift, const float* scale, const float* g_theta_r, const float* g_theta_w,
+                                       float* d_shift, float* d_scale, int64_t B, void* stream) {
+    MOG_REQUIRE(B >= 0, MOG_ERR_DIM, "thetas: B=%lld", (long long)B);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(shift && scale && g_theta_r && g_theta_w && d_shift && d_scale, MOG_ERR_NULL, "thetas backward: NULL pointer");
+    air_thetas_bwd<<<air_blocks(B), kAirThreads, 0, (cudaStream_t)stream>>>(shift, scale, g_theta_r, g_theta_w, d_shift, d_scale, B);
+    MOG_CUDA_LAUNCH_CHECK("air_thetas_bwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_zpres_forward(const float* log_odds, const float* u, const float* stop_in, float temperature,
+                                     float threshold, float* y_pre, float* z_pres, float* stop_out, unsigned char* active_prev,
+                                     unsigned char* active, int64_t B, void* stream) {
+    MOG_REQUIRE(B >= 0 && temperature > 0.0f, MOG_ERR_DIM, "zpres: B=%lld temperature=%g", (long long)B, (double)temperature);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(log_odds && u && stop_in && y_pre && z_pres && stop_out && active_prev && active, MOG_ERR_NULL,
+                "zpres forward: NULL pointer");
+    air_zpres_fwd<<<air_blocks(B), kAirThreads, 0, (cudaStream_t)stream>>>(log_odds, u, stop_in, temperature, threshold, y_pre,
+                                                                         z_pres, stop_out, active_prev, active, B);
+    MOG_CUDA_LAUNCH_CHECK("air_zpres_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_zpres_backward(const float* z_pres, const float* g_y, const float* g_z, float temperature,
+                                      float* d_log_odds, int64_t B, void* stream) {
+    MOG_REQUIRE(B >= 0 && temperature > 0.0f, MOG_ERR_DIM, "zpres: B=%lld temperature=%g", (long long)B, (double)temperature);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(z_pres && d_log_odds, MOG_ERR_NULL, "zpres backward: NULL pointer");
+    air_zpres_bwd<<<air_blocks(B), kAirThreads, 0, (cudaStream_t)stream>>>(z_pres, g_y, g_z, temperature, d_log_odds, B);
+    MOG_CUDA_LAUNCH_CHECK("air_zpres_bwd");
+    return MOG_OK;
+}

@@ -25,6 +25,29 @@ class OracleOps:
         r = torch.clamp(canvas, 0.0, 1.0)                                   # air_number_bbox_location.py:947-948
         return -(images * torch.log(r + 1e-10) + (1.0 - images) * torch.log(1.0 - r + 1e-10)).sum(1)   # :954-959
 
+    # per-step elementwise math, written out op for op like the reference
+    def gauss_sample(self, mean, logvar, eps, act=None):
+        latent = mean + eps * torch.sqrt(torch.exp(logvar))            # _sample_from_mvn, air_number_bbox_location.py:180-184
+        if act == "tanh":
+            return latent, torch.tanh(latent)                          # :435
+        if act == "sigmoid":
+            return latent, torch.sigmoid(latent)                       # :458
+        return latent, None
+
+    def thetas(self, inf_shift, inf_scale):
+        s, x, y = inf_scale[:, 0], inf_shift[:, 0], inf_shift[:, 1]
+        zero = torch.zeros_like(s)
+        theta_r = torch.stack([s, zero, x, zero, s, y], 1)                                   # :511-531
+        theta_w = torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1)             # :563-584
+        return theta_r, theta_w
+
+    def zpres(self, log_odds, u, stop_sum, temperature, threshold):
+        y_pre = (log_odds + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temperature   # concrete.py:20-27
+        z_pres = torch.sigmoid(y_pre)                                                        # :631
+        active_prev = stop_sum < threshold                                                   # :698-702 (previous stop_sum)
+        stop_new = stop_sum + (1.0 - z_pres)                                                 # :712
+        return y_pre, z_pres, stop_new, active_prev, stop_new < threshold
+
     def asr(self, cfg, log_odds, shifts, scales):
         pbar = None
         if cfg.constrains_margin_gamma > 1e-8:

@@ -1,0 +1,77 @@
+"""GPU parity of the fused per-step elementwise kernels (csrc/mog_air.cu) against the op-for-op torch restatement in
+oracle/air_ops.py (values and autograd gradients, fp64 yardstick)."""
+import numpy as np
+import pytest
+import torch
+
+from mog_asr_b200.air import fused
+from oracle.air_ops import OracleOps
+
+pytestmark = pytest.mark.gpu
+REF = OracleOps()
+
+
+def _check(got, ref, rtol=2e-6, atol=1e-7):
+    np.testing.assert_allclose(got.detach().cpu().double().numpy(), ref.detach().cpu().numpy(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("act", [None, "tanh", "sigmoid"])
+@pytest.mark.parametrize("shape", [(64, 2), (256, 1), (33, 50)])
+def test_gauss_sample(cuda_device, act, shape):
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    mean = torch.randn(shape, device=cuda_device, generator=g).requires_grad_(True)
+    lv = (torch.randn(shape, device=cuda_device, generator=g) * 0.7).requires_grad_(True)
+    eps = torch.randn(shape, device=cuda_device, generator=g)
+    gl, gs = torch.randn(shape, device=cuda_device, generator=g), torch.randn(shape, device=cuda_device, generator=g)
+    lat, sq = fused.gauss_sample(mean, lv, eps, act)
+    (lat * gl).sum().backward() if act is None else ((lat * gl).sum() + (sq * gs).sum()).backward()
+    m64, l64 = mean.detach().double().requires_grad_(True), lv.detach().double().requires_grad_(True)
+    rlat, rsq = REF.gauss_sample(m64, l64, eps.double(), act)
+    (rlat * gl.double()).sum().backward() if act is None else ((rlat * gl.double()).sum() + (rsq * gs.double()).sum()).backward()
+    _check(lat, rlat)
+    if act is not None:
+        _check(sq, rsq)
+    else:
+        assert sq is None
+    _check(mean.grad, m64.grad, rtol=1e-5, atol=1e-6)
+    _check(lv.grad, l64.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_thetas(cuda_device):
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    B = 300
+    sh = torch.tanh(torch.randn((B, 2), device=cuda_device, generator=g)).requires_grad_(True)
+    sc = torch.sigmoid(torch.randn((B, 1), device=cuda_device, generator=g) - 1).requires_grad_(True)
+    gr, gw = torch.randn((B, 6), device=cuda_device, generator=g), torch.randn((B, 6), device=cuda_device, generator=g)
+    tr, tw = fused.thetas(sh, sc)
+    ((tr * gr).sum() + (tw * gw).sum()).backward()
+    sh32, sc32 = sh.detach().clone().requires_grad_(True), sc.detach().clone().requires_grad_(True)
+    rr, rw = REF.thetas(sh32, sc32)                          # fp32: the forward must be bit-identical (fp32 divides)
+    assert torch.equal(tr, rr) and torch.equal(tw, rw)
+    sh64, sc64 = sh.detach().double().requires_grad_(True), sc.detach().double().requires_grad_(True)
+    r64, w64 = REF.thetas(sh64, sc64)
+    ((r64 * gr.double()).sum() + (w64 * gw.double()).sum()).backward()
+    _check(sh.grad, sh64.grad, rtol=1e-5, atol=1e-5)
+    _check(sc.grad.reshape(-1), sc64.grad.reshape(-1), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("temp", [0.1, 1.0])
+def test_zpres(cuda_device, temp):
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    B = 513
+    lo = (torch.randn(B, device=cuda_device, generator=g) * 2).requires_grad_(True)
+    u = torch.rand(B, device=cuda_device, generator=g).clamp(1e-4, 1 - 1e-4)
+    stop = torch.rand(B, device=cuda_device, generator=g) * 1.5
+    gy, gz = torch.randn(B, device=cuda_device, generator=g), torch.randn(B, device=cuda_device, generator=g)
+    y, z, s1, ap, ac = fused.zpres(lo, u, stop, temp, 0.9)
+    ((y * gy).sum() + (z * gz).sum()).backward()
+    lo64 = lo.detach().double().requires_grad_(True)
+    ry, rz, rs, rap, rac = REF.zpres(lo64, u.double(), stop.double(), temp, 0.9)
+    ((ry * gy.double()).sum() + (rz * gz.double()).sum()).backward()
+    _check(y, ry, rtol=1e-5, atol=1e-5)
+    _check(z, rz, rtol=1e-5, atol=1e-6)
+    _check(s1, rs, rtol=1e-6, atol=1e-6)
+    assert torch.equal(ap, rap)
+    close = (rs - 0.9).abs() < 1e-5                         # the mask may differ only where stop_sum sits on the threshold
+    assert torch.equal(ac[~close], rac[~close])
+    _check(lo.grad, lo64.grad, rtol=1e-5, atol=1e-6)
