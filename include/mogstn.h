@@ -153,6 +153,13 @@ MOG_API int mog_air_zpres_forward(const float* log_odds, const float* u, const f
 MOG_API int mog_air_zpres_backward(const float* z_pres, const float* g_y, const float* g_z, float temperature,
                            float* d_log_odds, int64_t B, void* stream);
 
+/* LSTM cell pointwise part (tf.nn.rnn_cell.LSTMCell, air_number_bbox_location.py:865-872): gates [B][4H] in the order
+ * i, j, f, o; c' = sigmoid(f + 1)*c + sigmoid(i)*tanh(j); h' = sigmoid(o)*tanh(c').  backward: g_h / g_c nullable. */
+MOG_API int mog_air_lstm_pointwise_forward(const float* gates, const float* c_prev, float* c_new, float* h_new, int64_t B,
+                                   int H, void* stream);
+MOG_API int mog_air_lstm_pointwise_backward(const float* gates, const float* c_prev, const float* c_new, const float* g_h,
+                                    const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,3 +121,37 @@ def zpres(log_odds, u, stop_sum, temperature, threshold):
     for t, n in ((log_odds, "log_odds"), (u, "u"), (stop_sum, "stop_sum")):
         _need_cuda(t, n)
     return _ZPres.apply(log_odds.float().contiguous(), u.float().contiguous(), stop_sum.detach().float().contiguous(), temperature, threshold)
+
+
+class _LstmPointwise(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gates, c_prev):
+        L = _lib.load()
+        B, H = c_prev.shape
+        c_new, h_new = torch.empty_like(c_prev), torch.empty_like(c_prev)
+        with torch.cuda.device(gates.device):
+            _lib.check(L.mog_air_lstm_pointwise_forward(_p(gates), _p(c_prev), _p(c_new), _p(h_new), B, H, _stream(gates)),
+                       "mog_air_lstm_pointwise_forward")
+        ctx.save_for_backward(gates, c_prev, c_new)
+        return c_new, h_new
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_c, g_h):
+        gates, c_prev, c_new = ctx.saved_tensors
+        L = _lib.load()
+        B, H = c_prev.shape
+        g_c = g_c.contiguous() if g_c is not None else None
+        g_h = g_h.contiguous() if g_h is not None else None
+        d_gates, d_c_prev = torch.empty_like(gates), torch.empty_like(c_prev)
+        with torch.cuda.device(gates.device):
+            _lib.check(L.mog_air_lstm_pointwise_backward(_p(gates), _p(c_prev), _p(c_new), _p(g_h), _p(g_c), _p(d_gates),
+                                                         _p(d_c_prev), B, H, _stream(gates)), "mog_air_lstm_pointwise_backward")
+        return d_gates, d_c_prev
+
+
+def lstm_pointwise(gates, c_prev):
+    """``gates [B,4H]`` (i, j, f, o) and ``c_prev [B,H]`` -> ``(c_new, h_new)`` with ``forget_bias = 1``."""
+    _need_cuda(gates, "gates")
+    _need_cuda(c_prev, "c_prev")
+    return _LstmPointwise.apply(gates.float().contiguous(), c_prev.float().contiguous())

@@ -111,6 +111,13 @@ class CudaOps:
         return (torch.stack([s, zero, x, zero, s, y], 1),                                     # :511-531
                 torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1))               # :563-584
 
+    @property
+    def lstm_pointwise(self):
+        if not self.fused_pointwise:
+            return None
+        from .fused import lstm_pointwise
+        return lstm_pointwise
+
     def zpres(self, log_odds, u, stop_sum, temperature, threshold):
         if self.fused_pointwise:
             from .fused import zpres
@@ -132,7 +139,71 @@ class CudaOps:
                                 global_batch=self.global_batch)
 
 
-class LSTMCellTF(nn.Module):
+class _DeferredAffine(torch.autograd.Function):
+    """``y = base + x @ w`` (``w`` is ``[in, out]``; ``base`` is a bias vector or a per-row tensor) whose backward
+    returns only ``dx`` (and ``dbase`` when ``base`` is a tensor with rows) and stashes ``(x, dy)``: the weight /
+    bias gradients of a layer that is applied once per loop iteration are then formed by ONE GEMM over the
+    concatenated rows of all iterations (``flush``) instead of one GEMM + one reduction + two accumulations per
+    iteration.  Same sums, associated differently."""
+
+    @staticmethod
+    def forward(ctx, x, w, base, stash, base_is_bias):
+        ctx.save_for_backward(x, w)
+        ctx.stash, ctx.base_is_bias = stash, base_is_bias
+        return torch.addmm(base, x, w)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        ctx.stash.append((x, dy))
+        return dy @ w.t(), None, (None if ctx.base_is_bias else dy), None, None
+
+
+class _StepAffine:
+    """mixin: owns the stash of a layer that is applied once per loop iteration"""
+
+    def _init_defer(self):
+        self._stash, self.defer = [], False
+
+    def _affine(self, x, w_in_out, bias, base=None):
+        """x @ w + (base if given else bias); weight/bias gradients deferred when ``self.defer``."""
+        if not (self.defer and torch.is_grad_enabled()):
+            return torch.addmm(bias if base is None else base, x, w_in_out)
+        return _DeferredAffine.apply(x, w_in_out, bias if base is None else base, self._stash, base is None)
+
+    def flush(self, weight_grad_in_out, bias_grad, bias_from_stash=True):
+        """accumulate the deferred gradients into the given .grad views and clear the stash"""
+        if not self._stash:
+            return
+        with torch.no_grad():
+            X = torch.cat([x.detach() for x, _ in self._stash], 0)
+            DY = torch.cat([dy.detach() for _, dy in self._stash], 0)
+            weight_grad_in_out.addmm_(X.t(), DY)
+            if bias_from_stash and bias_grad is not None:
+                bias_grad.add_(DY.sum(0))
+        self._stash.clear()
+
+
+class StepLinear(nn.Module, _StepAffine):
+    """``tf.layers.dense`` / ``layers.fully_connected`` (glorot-uniform kernel, zero bias) with deferrable weight
+    gradients; parameters keep the nn.Linear layout (``weight [out, in]``, ``bias [out]``)."""
+
+    def __init__(self, i, o):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(o, i))
+        self.bias = nn.Parameter(torch.zeros(o))
+        nn.init.xavier_uniform_(self.weight)
+        self._init_defer()
+
+    def forward(self, x):
+        return self._affine(x, self.weight.t(), self.bias)
+
+    def flush_grads(self):
+        self.flush(self.weight.grad.t(), self.bias.grad)
+
+
+class LSTMCellTF(nn.Module, _StepAffine):
     """``tf.nn.rnn_cell.LSTMCell(units)`` (:865-872): one kernel ``[in+units, 4*units]``, gate order i, j, f, o,
     ``forget_bias = 1.0`` added at run time, glorot-uniform kernel, zero bias  [TF-1.12 defaults]."""
 
@@ -142,19 +213,29 @@ class LSTMCellTF(nn.Module):
         self.kernel = nn.Parameter(torch.empty(input_size + units, 4 * units))
         self.bias = nn.Parameter(torch.zeros(4 * units))
         nn.init.xavier_uniform_(self.kernel)
+        self._init_defer()
+        self._static_width = 0
 
-    def forward(self, x, state, static_gates=None, static_width=0):
+    def flush_grads(self):
+        # with a static block the bias gradient flows through static_gates (ordinary autograd), not the stash
+        self.flush(self.kernel.grad[self._static_width:], self.bias.grad, bias_from_stash=(self._static_width == 0))
+
+    def forward(self, x, state, static_gates=None, static_width=0, pointwise=None):
         """``static_gates`` = ``x_static @ kernel[:static_width]`` for a leading block of the input that does not
         change between steps (the flattened image, ``:416-419``): it is computed once per training step instead of
         once per loop iteration -- the same sum, associated differently -- and ``x`` then holds only the rest."""
         c, h = state
+        self._static_width = static_width if static_gates is not None else 0
         if static_gates is None:
-            gates = torch.addmm(self.bias, torch.cat([x, h], 1), self.kernel)
+            gates = self._affine(torch.cat([x, h], 1), self.kernel, self.bias)
         else:
-            gates = torch.addmm(static_gates, torch.cat([x, h], 1), self.kernel[static_width:])
-        i, j, f, o = gates.chunk(4, 1)
-        c2 = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
-        h2 = torch.sigmoid(o) * torch.tanh(c2)
+            gates = self._affine(torch.cat([x, h], 1), self.kernel[static_width:], self.bias, base=static_gates)
+        if pointwise is not None:
+            c2, h2 = pointwise(gates, c)
+        else:
+            i, j, f, o = gates.chunk(4, 1)
+            c2 = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+            h2 = torch.sigmoid(o) * torch.tanh(c2)
         return h2, (c2, h2)
 
     def static_part(self, x_static):
@@ -165,10 +246,7 @@ class LSTMCellTF(nn.Module):
 
 def _dense(i, o):
     """``tf.layers.dense`` / ``layers.fully_connected`` defaults: glorot-uniform kernel, zero bias."""
-    l = nn.Linear(i, o)
-    nn.init.xavier_uniform_(l.weight)
-    nn.init.zeros_(l.bias)
-    return l
+    return StepLinear(i, o)
 
 
 class _MeanVar(nn.Module):
@@ -208,6 +286,18 @@ class AIRModel(nn.Module):
         if cfg.fix_steps is None:
             self.z_prior_h, self.z_prior = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)  # :609-615
         self.z_post_h, self.z_post = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)        # :620-623
+
+    # ---- deferred weight gradients (see _DeferredAffine) ------------------------------------------------------
+    def set_deferred_weight_grads(self, on: bool):
+        for m in self.modules():
+            if isinstance(m, _StepAffine):
+                m.defer = bool(on)
+                m._stash.clear()
+
+    def flush_weight_grads(self):
+        for m in self.modules():
+            if isinstance(m, _StepAffine):
+                m.flush_grads()
 
     # ---- pieces -------------------------------------------------------------------------------------------
     def _vae(self, window, eps):
@@ -271,6 +361,7 @@ class AIRModel(nn.Module):
         # the image block of the inference LSTM input is the same at every step: its 2500x1024 GEMM runs once
         img_gates, img_w = self.infer_cell.static_part(images)
 
+        lstm_pw = getattr(self.ops, "lstm_pointwise", None)   # fused gate math when the ops object offers it
         step = 0
         while step < cfg.max_steps:
             if not cfg.always_max_steps and step > 0:        # cond (:386-390); step 0 always runs (stop_sum = 0)
@@ -280,13 +371,14 @@ class AIRModel(nn.Module):
                 if not bool(flag):
                     break
             prev = torch.cat([prev_latent, prev_ss], -1)   # input of both cells besides the image / the state
-            out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w)  # :413-422
+            out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w,
+                                             pointwise=lstm_pw)                                             # :413-422
             sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
             shift_latent, inf_shift = self.ops.gauss_sample(sh_mean, sh_lv, noise("shift", step, (B, 2)), "tanh")    # :433-435
             sc_mean, sc_lv = self.inf_scale(out, shift_latent)                                              # :439-455
             scale_latent, inf_scale = self.ops.gauss_sample(sc_mean, sc_lv, noise("scale", step, (B, 1)), "sigmoid")  # :456-458
             ss_latent = torch.cat([shift_latent, scale_latent], -1)                                         # :463
-            gen_out, gen_state = self.gen_cell(prev, gen_state)                                             # :465-470
+            gen_out, gen_state = self.gen_cell(prev, gen_state, pointwise=lstm_pw)                          # :465-470
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
 
             theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)                                        # :511-531,:563-584

@@ -21,7 +21,7 @@ from .model import AIRConfig, AIRModel, CudaOps
 
 class Trainer:
     def __init__(self, cfg: AIRConfig, device, process_group=None, global_batch: Optional[int] = None, seed: int = 1235,
-                 ops=None, dtype=torch.float32):
+                 ops=None, dtype=torch.float32, defer_weight_grads=True):
         self.cfg, self.device, self.pg = cfg, torch.device(device), process_group
         self.world = dist.get_world_size(process_group) if process_group is not None else 1
         self.global_batch = global_batch
@@ -29,6 +29,7 @@ class Trainer:
         if ops is None:
             ops = CudaOps(process_group=process_group, global_batch=global_batch)
         self.model = AIRModel(cfg, ops).to(self.device, dtype)   # fp32 is the product; fp64 only for test oracles
+        self.defer_weight_grads = defer_weight_grads
         self.params = [p for p in self.model.parameters()]
         # flat gradient bucket: every p.grad is a view into it -> one all-reduce per step
         n = sum(p.numel() for p in self.params)
@@ -66,9 +67,12 @@ class Trainer:
         B = images.shape[0]
         nglobal = self.global_batch if self.global_batch is not None else B * self.world
         self.flat_grad.zero_()
+        self.model.set_deferred_weight_grads(self.defer_weight_grads)
         out = self.model(images, noise=noise or self._noise, any_reduce=self._any_reduce if self.pg is not None else None,
                          global_batch=nglobal, recon_loss_fn=recon_loss_fn)
         out["loss"].backward()
+        if self.defer_weight_grads:
+            self.model.flush_weight_grads()   # one GEMM per layer over all loop iterations' rows
         return out
 
     def reduce_gradients(self):

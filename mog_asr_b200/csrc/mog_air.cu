@@ -93,9 +93,72 @@ __global__ void air_zpres_bwd(const float* __restrict__ z_pres, const float* __r
     }
 }
 
+// LSTM cell pointwise part (tf.nn.rnn_cell.LSTMCell, :865-872): gates [B][4H] in the order i, j, f, o,
+// c' = sigmoid(f + 1)*c + sigmoid(i)*tanh(j),  h' = sigmoid(o)*tanh(c')   (forget_bias = 1)
+__global__ void air_lstm_fwd(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_new,
+                             float* __restrict__ h_new, long long B, int H) {
+    const long long n = B * (long long)H;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long b = k / H;
+        const int u = (int)(k - b * H);
+        const float* gr = gates + b * 4 * H;
+        const float i = 1.0f / (1.0f + expf(-gr[u])), j = tanhf(gr[H + u]);
+        const float f = 1.0f / (1.0f + expf(-(gr[2 * H + u] + 1.0f))), o = 1.0f / (1.0f + expf(-gr[3 * H + u]));
+        const float c = f * c_prev[k] + i * j;
+        c_new[k] = c;
+        h_new[k] = o * tanhf(c);
+    }
+}
+
+// g_h / g_c nullable (gradients w.r.t. h' and c'); d_gates [B][4H], d_c_prev [B][H] fully overwritten
+__global__ void air_lstm_bwd(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                             const float* __restrict__ g_h, const float* __restrict__ g_c, float* __restrict__ d_gates,
+                             float* __restrict__ d_c_prev, long long B, int H) {
+    const long long n = B * (long long)H;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long b = k / H;
+        const int u = (int)(k - b * H);
+        const float* gr = gates + b * 4 * H;
+        float* dg = d_gates + b * 4 * H;
+        const float i = 1.0f / (1.0f + expf(-gr[u])), j = tanhf(gr[H + u]);
+        const float f = 1.0f / (1.0f + expf(-(gr[2 * H + u] + 1.0f))), o = 1.0f / (1.0f + expf(-gr[3 * H + u]));
+        const float tc = tanhf(c_new[k]);
+        const float dh = g_h ? g_h[k] : 0.0f;
+        const float dc = (g_c ? g_c[k] : 0.0f) + dh * o * (1.0f - tc * tc);
+        dg[u] = dc * j * i * (1.0f - i);
+        dg[H + u] = dc * i * (1.0f - j * j);
+        dg[2 * H + u] = dc * c_prev[k] * f * (1.0f - f);
+        dg[3 * H + u] = dh * tc * o * (1.0f - o);
+        d_c_prev[k] = dc * f;
+    }
+}
+
 }  // namespace mog
 
 using namespace mog;
+
+extern "C" int mog_air_lstm_pointwise_forward(const float* gates, const float* c_prev, float* c_new, float* h_new, int64_t B,
+                                              int H, void* stream) {
+    MOG_REQUIRE(B >= 0 && H > 0, MOG_ERR_DIM, "lstm pointwise: B=%lld H=%d", (long long)B, H);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(gates && c_prev && c_new && h_new, MOG_ERR_NULL, "lstm pointwise forward: NULL pointer");
+    air_lstm_fwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, h_new, B, H);
+    MOG_CUDA_LAUNCH_CHECK("air_lstm_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_lstm_pointwise_backward(const float* gates, const float* c_prev, const float* c_new, const float* g_h,
+                                               const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H,
+                                               void* stream) {
+    MOG_REQUIRE(B >= 0 && H > 0, MOG_ERR_DIM, "lstm pointwise: B=%lld H=%d", (long long)B, H);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(gates && c_prev && c_new && d_gates && d_c_prev, MOG_ERR_NULL, "lstm pointwise backward: NULL pointer");
+    air_lstm_bwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, g_h, g_c, d_gates,
+                                                                                       d_c_prev, B, H);
+    MOG_CUDA_LAUNCH_CHECK("air_lstm_bwd");
+    return MOG_OK;
+}
+
 
 extern "C" int mog_air_gauss_sample_forward(const float* mean, const float* logvar, const float* eps, float* latent,
                                             float* squashed, int64_t n, int act, void* stream) {

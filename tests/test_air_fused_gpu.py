@@ -75,3 +75,22 @@ def test_zpres(cuda_device, temp):
     close = (rs - 0.9).abs() < 1e-5                         # the mask may differ only where stop_sum sits on the threshold
     assert torch.equal(ac[~close], rac[~close])
     _check(lo.grad, lo64.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_lstm_pointwise(cuda_device):
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    B, Hh = 37, 256
+    gates = torch.randn((B, 4 * Hh), device=cuda_device, generator=g).requires_grad_(True)
+    c = torch.randn((B, Hh), device=cuda_device, generator=g).requires_grad_(True)
+    gc, gh = torch.randn((B, Hh), device=cuda_device, generator=g), torch.randn((B, Hh), device=cuda_device, generator=g)
+    c2, h2 = fused.lstm_pointwise(gates, c)
+    ((c2 * gc).sum() + (h2 * gh).sum()).backward()
+    g64, c64 = gates.detach().double().requires_grad_(True), c.detach().double().requires_grad_(True)
+    i, j, f, o = g64.chunk(4, 1)                                   # LSTMCellTF.forward, written out
+    rc = torch.sigmoid(f + 1.0) * c64 + torch.sigmoid(i) * torch.tanh(j)
+    rh = torch.sigmoid(o) * torch.tanh(rc)
+    ((rc * gc.double()).sum() + (rh * gh.double()).sum()).backward()
+    _check(c2, rc, rtol=1e-5, atol=1e-6)
+    _check(h2, rh, rtol=1e-5, atol=1e-6)
+    _check(gates.grad, g64.grad, rtol=1e-5, atol=1e-6)
+    _check(c.grad, c64.grad, rtol=1e-5, atol=1e-6)

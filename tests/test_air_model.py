@@ -74,6 +74,22 @@ def test_stacked_kl_equals_per_step_form(flags):
     assert float((g1[fin] - g0[fin]).abs().max()) <= 1e-5 * float(g0[fin].abs().max())
 
 
+def test_deferred_weight_gradients_equal_autograd():
+    """One GEMM per layer over the concatenated rows of all loop iterations == per-iteration autograd accumulation."""
+    cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0)
+    images, _ = make_images(6, 50, seed=3)
+    grads = []
+    for defer in (False, True):
+        tr = Trainer(cfg, "cpu", ops=OracleOps(), seed=5, defer_weight_grads=defer)
+        tr.forward_backward(images, noise=SeededNoise(4, 6))
+        grads.append(tr.flat_grad.clone())
+    g0, g1 = grads
+    fin = torch.isfinite(g0)
+    assert torch.equal(torch.isfinite(g1), fin)
+    assert float((g1[fin] - g0[fin]).abs().max()) <= 1e-5 * float(g0[fin].abs().max())
+    assert float(g0[fin].abs().max()) > 0
+
+
 def _dp_worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
