@@ -160,6 +160,27 @@ MOG_API int mog_air_lstm_pointwise_forward(const float* gates, const float* c_pr
 MOG_API int mog_air_lstm_pointwise_backward(const float* gates, const float* c_prev, const float* c_new, const float* g_h,
                                     const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H, void* stream);
 
+/* The four KL terms of the ELBO for all executed steps at once (air_number_bbox_location.py:690-787, masked and summed
+ * as at :930-935).  Inputs are [T][B][..] stacks: y_pre / prior_lo / post_lo [T][B] (Concrete KL, air/concrete.py:30-64,
+ * equal temperatures), active_prev / active [T][B] bytes (stopping_sum < threshold before / after the step's update),
+ * sc_mean / sc_lv [T][B] (fixed scale prior), sh_* and g_sh_* [T][B][2] (learned shift prior), v_mean / v_lv [T][B][L].
+ * kl[b] = sum_t active_prev*z_pres_kl + active*(scale_kl + shift_kl + vae_kl); components [B][4] (nullable) holds the four
+ * per-image sums the reference logs.  Backward: every d_* is fully overwritten with g_kl[b] * d kl[b] / d input. */
+MOG_API int mog_air_kl_forward(const float* y_pre, const float* prior_lo, const float* post_lo, const unsigned char* active_prev,
+                       const unsigned char* active, const float* sc_mean, const float* sc_lv, const float* sh_mean,
+                       const float* sh_lv, const float* g_sh_mean, const float* g_sh_lv, const float* v_mean,
+                       const float* v_lv, int64_t B, int T, int L, float temperature, float scale_prior_mean,
+                       float scale_prior_var, float vae_prior_mean, float vae_prior_var, float* kl, float* components,
+                       void* stream);
+MOG_API int mog_air_kl_backward(const float* y_pre, const float* prior_lo, const float* post_lo, const unsigned char* active_prev,
+                        const unsigned char* active, const float* sc_mean, const float* sc_lv, const float* sh_mean,
+                        const float* sh_lv, const float* g_sh_mean, const float* g_sh_lv, const float* v_mean,
+                        const float* v_lv, int64_t B, int T, int L, float temperature, float scale_prior_mean,
+                        float scale_prior_var, float vae_prior_mean, float vae_prior_var, const float* g_kl,
+                        float* d_y_pre, float* d_prior_lo, float* d_post_lo, float* d_sc_mean, float* d_sc_lv,
+                        float* d_sh_mean, float* d_sh_lv, float* d_g_sh_mean, float* d_g_sh_lv, float* d_v_mean,
+                        float* d_v_lv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mog_air_zpres_backward": [_vp, _vp, _vp, _f32, _vp, _i64, _vp],
     "mog_air_lstm_pointwise_forward": [_vp, _vp, _vp, _vp, _i64, _int, _vp],
     "mog_air_lstm_pointwise_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_kl_forward": [_vp] * 13 + [_i64, _int, _int, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
+    "mog_air_kl_backward": [_vp] * 13 + [_i64, _int, _int, _f32, _f32, _f32, _f32, _f32] + [_vp] * 12 + [_vp],
     "mog_asr_reg_colsum": [_vp, _vp, _i64, _int, _vp],
     "mog_asr_reg_forward": [_vp, _vp, _vp, _vp, _f32, _i64, _int, ctypes.POINTER(AsrConfig), _vp, _vp, _vp, _vp],
     "mog_asr_reg_backward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _int, ctypes.POINTER(AsrConfig), _vp, _vp, _vp, _vp],

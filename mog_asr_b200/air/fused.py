@@ -155,3 +155,64 @@ def lstm_pointwise(gates, c_prev):
     _need_cuda(gates, "gates")
     _need_cuda(c_prev, "c_prev")
     return _LstmPointwise.apply(gates.float().contiguous(), c_prev.float().contiguous())
+
+
+_KL_KEYS = ("y_pre", "prior_lo", "post_lo", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "g_sh_mean", "g_sh_lv", "v_mean", "v_lv")
+
+
+class _KlTerms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, active_prev, active, consts, *tensors):
+        L = _lib.load()
+        y_pre = tensors[0]
+        T, B = y_pre.shape
+        Ld = tensors[9].shape[-1]
+        temp, scm, scv, vm, vv = consts
+        kl = torch.empty(B, dtype=torch.float32, device=y_pre.device)
+        comps = torch.empty((B, 4), dtype=torch.float32, device=y_pre.device)
+        t = dict(zip(_KL_KEYS, tensors))
+        with torch.cuda.device(y_pre.device):
+            _lib.check(L.mog_air_kl_forward(
+                _p(t["y_pre"]), _p(t["prior_lo"]), _p(t["post_lo"]), _p(active_prev), _p(active), _p(t["sc_mean"]), _p(t["sc_lv"]),
+                _p(t["sh_mean"]), _p(t["sh_lv"]), _p(t["g_sh_mean"]), _p(t["g_sh_lv"]), _p(t["v_mean"]), _p(t["v_lv"]),
+                B, T, Ld, temp, scm, scv, vm, vv, _p(kl), _p(comps), _stream(y_pre)), "mog_air_kl_forward")
+        ctx.save_for_backward(active_prev, active, *tensors)
+        ctx.consts, ctx.dims = consts, (B, T, Ld)
+        ctx.mark_non_differentiable(comps)
+        return kl, comps
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_kl, _g_comps):
+        active_prev, active, *tensors = ctx.saved_tensors
+        L = _lib.load()
+        B, T, Ld = ctx.dims
+        temp, scm, scv, vm, vv = ctx.consts
+        t = dict(zip(_KL_KEYS, tensors))
+        d = {k: torch.empty_like(v) for k, v in t.items()}
+        g_kl = g_kl.to(torch.float32).contiguous()
+        with torch.cuda.device(g_kl.device):
+            _lib.check(L.mog_air_kl_backward(
+                _p(t["y_pre"]), _p(t["prior_lo"]), _p(t["post_lo"]), _p(active_prev), _p(active), _p(t["sc_mean"]), _p(t["sc_lv"]),
+                _p(t["sh_mean"]), _p(t["sh_lv"]), _p(t["g_sh_mean"]), _p(t["g_sh_lv"]), _p(t["v_mean"]), _p(t["v_lv"]),
+                B, T, Ld, temp, scm, scv, vm, vv, _p(g_kl),
+                _p(d["y_pre"]), _p(d["prior_lo"]), _p(d["post_lo"]), _p(d["sc_mean"]), _p(d["sc_lv"]), _p(d["sh_mean"]), _p(d["sh_lv"]),
+                _p(d["g_sh_mean"]), _p(d["g_sh_lv"]), _p(d["v_mean"]), _p(d["v_lv"]), _stream(g_kl)), "mog_air_kl_backward")
+        return (None, None, None) + tuple(d[k] for k in _KL_KEYS)
+
+
+def kl_terms(stacks, temperature, scale_prior_mean, scale_prior_var, vae_prior_mean, vae_prior_var):
+    """``stacks``: dict of ``[T,B,..]`` tensors with the keys of ``_KL_KEYS`` plus boolean ``active_prev`` / ``active``.
+    Returns ``(kl [B], components [B,4])`` -- the masked sum over steps of the four KL terms and the four separate sums."""
+    ts = []
+    for k in _KL_KEYS:
+        v = stacks[k]
+        _need_cuda(v, k)
+        v = v.to(torch.float32)
+        if k in ("sc_mean", "sc_lv"):
+            v = v.reshape(v.shape[0], v.shape[1])
+        ts.append(v.contiguous())
+    ap = stacks["active_prev"].to(torch.bool).contiguous()
+    ac = stacks["active"].to(torch.bool).contiguous()
+    consts = (float(temperature), float(scale_prior_mean), float(scale_prior_var), float(vae_prior_mean), float(vae_prior_var))
+    return _KlTerms.apply(ap, ac, consts, *ts)

@@ -111,6 +111,14 @@ class CudaOps:
         return (torch.stack([s, zero, x, zero, s, y], 1),                                     # :511-531
                 torch.stack([1.0 / s, zero, -x / s, zero, 1.0 / s, -y / s], 1))               # :563-584
 
+    def kl_terms(self, stacks, cfg):
+        """masked sum over steps of the four KL terms, one kernel each way; None = use the framework-op form"""
+        if not self.fused_pointwise:
+            return None
+        from .fused import kl_terms
+        return kl_terms(stacks, cfg.z_pres_temperature, cfg.scale_prior_mean, cfg.scale_prior_variance, cfg.vae_prior_mean,
+                        cfg.vae_prior_variance)[0]
+
     @property
     def lstm_pointwise(self):
         if not self.fused_pointwise:
@@ -414,6 +422,10 @@ class AIRModel(nn.Module):
         T = step
         if cfg.stacked_kl:
             H_ = {k: torch.stack(v, 0) for k, v in hist.items()}                                            # [T, B, ...]
+            fused_kl = self.ops.kl_terms(H_, cfg) if hasattr(self.ops, "kl_terms") else None
+        if cfg.stacked_kl and fused_kl is not None:
+            elbo = fused_kl                                                                                 # :690-787,:930-935 fused
+        elif cfg.stacked_kl:
             z_kl = self._concrete_kl(H_["y_pre"], H_["prior_lo"], H_["post_lo"], temp)
             scale_kl, shift_kl, vae_kl = self._gaussian_kls(H_["sc_mean"], H_["sc_lv"], H_["sh_mean"], H_["sh_lv"],
                                                             H_["g_sh_mean"], H_["g_sh_lv"], H_["v_mean"], H_["v_lv"])

@@ -133,9 +133,154 @@ __global__ void air_lstm_bwd(const float* __restrict__ gates, const float* __res
     }
 }
 
+// ---- the four KL terms of the ELBO, all steps at once ----------------------------------------------------------
+// Inputs are [T][B][...] stacks of the per-step tensors; output kl[b] = sum_t ( mask_prev*z_pres_kl + mask*(scale_kl +
+// shift_kl + vae_kl) ) (air_number_bbox_location.py:690-787 masked and summed as at :930-935), plus the four separate
+// per-image sums the reference logs (components [B][4]: z_pres, scale, shift, vae).
+struct KlArgs {
+    const float *y_pre, *prior_lo, *post_lo;              // [T][B]
+    const unsigned char *active_prev, *active;            // [T][B]
+    const float *sc_mean, *sc_lv;                         // [T][B]      (scale latent is 1-d)
+    const float *sh_mean, *sh_lv, *g_sh_mean, *g_sh_lv;   // [T][B][2]
+    const float *v_mean, *v_lv;                           // [T][B][L]
+    long long B;
+    int T, L;
+    float temp, sc_prior_mean, sc_prior_var, v_prior_mean, v_prior_var;
+    // forward
+    float *kl, *components;
+    // backward
+    const float* g_kl;                                    // [B]
+    float *d_y_pre, *d_prior_lo, *d_post_lo, *d_sc_mean, *d_sc_lv, *d_sh_mean, *d_sh_lv, *d_g_sh_mean, *d_g_sh_lv, *d_v_mean,
+        *d_v_lv;
+};
+
+__device__ __forceinline__ float lse0(float a) { return fmaxf(a, 0.0f) + log1pf(expf(-fabsf(a))); }   // log(1 + e^a)
+__device__ __forceinline__ float sigm(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(128) air_kl_kernel(const KlArgs a) {
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const float log_temp = logf(a.temp + 10e-10f);
+    const float g = BACKWARD ? a.g_kl[b] : 0.0f;
+    float kz = 0.f, ksc = 0.f, ksh = 0.f, kv = 0.f;
+    for (int t = 0; t < a.T; ++t) {
+        const long long k = (long long)t * a.B + b;
+        const bool mp = a.active_prev[k] != 0, m = a.active[k] != 0;
+        // Concrete KL (air/concrete.py:30-64 with equal temperatures)
+        const float y = a.y_pre[k], lp = a.prior_lo[k], lq = a.post_lo[k];
+        const float ap = -y * a.temp + lp, aq = -y * a.temp + lq;
+        if (!BACKWARD) {
+            const float log_prior = log_temp - y * (a.temp + 1.0f) + lp - 2.0f * lse0(ap);
+            const float log_post = log_temp - y * (a.temp + 1.0f) + lq - 2.0f * lse0(aq);
+            if (mp) kz += log_post - log_prior;
+        } else {
+            const float gz = mp ? g : 0.0f;
+            const float sp = sigm(ap), sq = sigm(aq);
+            a.d_y_pre[k] = gz * 2.0f * a.temp * (sq - sp);
+            a.d_post_lo[k] = gz * (1.0f - 2.0f * sq);
+            a.d_prior_lo[k] = -gz * (1.0f - 2.0f * sp);
+        }
+        const float gm = m ? g : 0.0f;
+        {   // scale KL against the fixed prior (:731-736)
+            const float mu = a.sc_mean[k], lv = a.sc_lv[k], ev = expf(lv), dm = mu - a.sc_prior_mean;
+            if (!BACKWARD) {
+                if (m) ksc += 0.5f * (logf(a.sc_prior_var) - lv - 1.0f + ev / a.sc_prior_var + dm * dm / a.sc_prior_var);
+            } else {
+                a.d_sc_mean[k] = gm * dm / a.sc_prior_var;
+                a.d_sc_lv[k] = gm * 0.5f * (ev / a.sc_prior_var - 1.0f);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {   // shift KL against the learned prior (:750-755)
+            const long long q = 2 * k + c;
+            const float mu = a.sh_mean[q], lv = a.sh_lv[q], gmu = a.g_sh_mean[q], glv = a.g_sh_lv[q];
+            const float gvar = expf(glv), ev = expf(lv), dm = mu - gmu;
+            if (!BACKWARD) {
+                if (m) ksh += 0.5f * (glv - lv - 1.0f + ev / gvar + dm * dm / gvar);
+            } else {
+                a.d_sh_mean[q] = gm * dm / gvar;
+                a.d_sh_lv[q] = gm * 0.5f * (ev / gvar - 1.0f);
+                a.d_g_sh_mean[q] = -gm * dm / gvar;
+                a.d_g_sh_lv[q] = gm * 0.5f * (1.0f - ev / gvar - dm * dm / gvar);
+            }
+        }
+        for (int c = 0; c < a.L; ++c) {   // VAE latent KL (:769-774)
+            const long long q = k * a.L + c;
+            const float mu = a.v_mean[q], lv = a.v_lv[q], ev = expf(lv), dm = mu - a.v_prior_mean;
+            if (!BACKWARD) {
+                if (m) kv += 0.5f * (logf(a.v_prior_var) - lv - 1.0f + ev / a.v_prior_var + dm * dm / a.v_prior_var);
+            } else {
+                a.d_v_mean[q] = gm * dm / a.v_prior_var;
+                a.d_v_lv[q] = gm * 0.5f * (ev / a.v_prior_var - 1.0f);
+            }
+        }
+    }
+    if (!BACKWARD) {
+        a.kl[b] = ((kz + ksc) + ksh) + kv;
+        if (a.components) {
+            float* c = a.components + 4 * b;
+            c[0] = kz; c[1] = ksc; c[2] = ksh; c[3] = kv;
+        }
+    }
+}
+
 }  // namespace mog
 
 using namespace mog;
+
+static int check_kl(const KlArgs& a) {
+    MOG_REQUIRE(a.B >= 0 && a.T > 0 && a.L > 0 && a.temp > 0.0f && a.sc_prior_var > 0.0f && a.v_prior_var > 0.0f, MOG_ERR_DIM,
+                "air kl: B=%lld T=%d L=%d temp=%g", a.B, a.T, a.L, (double)a.temp);
+    MOG_REQUIRE(a.B == 0 || (a.y_pre && a.prior_lo && a.post_lo && a.active_prev && a.active && a.sc_mean && a.sc_lv && a.sh_mean &&
+                             a.sh_lv && a.g_sh_mean && a.g_sh_lv && a.v_mean && a.v_lv), MOG_ERR_NULL, "air kl: NULL input pointer");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_kl_forward(const float* y_pre, const float* prior_lo, const float* post_lo, const unsigned char* active_prev,
+                                  const unsigned char* active, const float* sc_mean, const float* sc_lv, const float* sh_mean,
+                                  const float* sh_lv, const float* g_sh_mean, const float* g_sh_lv, const float* v_mean,
+                                  const float* v_lv, int64_t B, int T, int L, float temperature, float scale_prior_mean,
+                                  float scale_prior_var, float vae_prior_mean, float vae_prior_var, float* kl, float* components,
+                                  void* stream) {
+    KlArgs a{};
+    a.y_pre = y_pre; a.prior_lo = prior_lo; a.post_lo = post_lo; a.active_prev = active_prev; a.active = active;
+    a.sc_mean = sc_mean; a.sc_lv = sc_lv; a.sh_mean = sh_mean; a.sh_lv = sh_lv; a.g_sh_mean = g_sh_mean; a.g_sh_lv = g_sh_lv;
+    a.v_mean = v_mean; a.v_lv = v_lv; a.B = B; a.T = T; a.L = L; a.temp = temperature; a.sc_prior_mean = scale_prior_mean;
+    a.sc_prior_var = scale_prior_var; a.v_prior_mean = vae_prior_mean; a.v_prior_var = vae_prior_var; a.kl = kl; a.components = components;
+    if (int rc = check_kl(a)) return rc;
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(kl, MOG_ERR_NULL, "air kl forward: NULL output");
+    air_kl_kernel<false><<<(int)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("air_kl_kernel<fwd>");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_kl_backward(const float* y_pre, const float* prior_lo, const float* post_lo, const unsigned char* active_prev,
+                                   const unsigned char* active, const float* sc_mean, const float* sc_lv, const float* sh_mean,
+                                   const float* sh_lv, const float* g_sh_mean, const float* g_sh_lv, const float* v_mean,
+                                   const float* v_lv, int64_t B, int T, int L, float temperature, float scale_prior_mean,
+                                   float scale_prior_var, float vae_prior_mean, float vae_prior_var, const float* g_kl,
+                                   float* d_y_pre, float* d_prior_lo, float* d_post_lo, float* d_sc_mean, float* d_sc_lv,
+                                   float* d_sh_mean, float* d_sh_lv, float* d_g_sh_mean, float* d_g_sh_lv, float* d_v_mean,
+                                   float* d_v_lv, void* stream) {
+    KlArgs a{};
+    a.y_pre = y_pre; a.prior_lo = prior_lo; a.post_lo = post_lo; a.active_prev = active_prev; a.active = active;
+    a.sc_mean = sc_mean; a.sc_lv = sc_lv; a.sh_mean = sh_mean; a.sh_lv = sh_lv; a.g_sh_mean = g_sh_mean; a.g_sh_lv = g_sh_lv;
+    a.v_mean = v_mean; a.v_lv = v_lv; a.B = B; a.T = T; a.L = L; a.temp = temperature; a.sc_prior_mean = scale_prior_mean;
+    a.sc_prior_var = scale_prior_var; a.v_prior_mean = vae_prior_mean; a.v_prior_var = vae_prior_var; a.g_kl = g_kl;
+    a.d_y_pre = d_y_pre; a.d_prior_lo = d_prior_lo; a.d_post_lo = d_post_lo; a.d_sc_mean = d_sc_mean; a.d_sc_lv = d_sc_lv;
+    a.d_sh_mean = d_sh_mean; a.d_sh_lv = d_sh_lv; a.d_g_sh_mean = d_g_sh_mean; a.d_g_sh_lv = d_g_sh_lv; a.d_v_mean = d_v_mean;
+    a.d_v_lv = d_v_lv;
+    if (int rc = check_kl(a)) return rc;
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(g_kl && d_y_pre && d_prior_lo && d_post_lo && d_sc_mean && d_sc_lv && d_sh_mean && d_sh_lv && d_g_sh_mean && d_g_sh_lv &&
+                d_v_mean && d_v_lv, MOG_ERR_NULL, "air kl backward: NULL pointer");
+    air_kl_kernel<true><<<(int)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("air_kl_kernel<bwd>");
+    return MOG_OK;
+}
+
 
 extern "C" int mog_air_lstm_pointwise_forward(const float* gates, const float* c_prev, float* c_new, float* h_new, int64_t B,
                                               int H, void* stream) {

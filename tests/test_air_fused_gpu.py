@@ -94,3 +94,34 @@ def test_lstm_pointwise(cuda_device):
     _check(h2, rh, rtol=1e-5, atol=1e-6)
     _check(gates.grad, g64.grad, rtol=1e-5, atol=1e-6)
     _check(c.grad, c64.grad, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("T", [6, 3])
+def test_kl_terms(cuda_device, T):
+    """fused KL kernel vs the model's framework-op formulas (AIRModel._concrete_kl / _gaussian_kls) in fp64"""
+    from mog_asr_b200.air import AIRModel, config_from_flags
+    cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0)
+    model = AIRModel(cfg, ops=REF)
+    g = torch.Generator(device=cuda_device).manual_seed(6)
+    B, Ld = 65, cfg.vae_latent_dimensions
+    shp = dict(y_pre=(T, B), prior_lo=(T, B), post_lo=(T, B), sc_mean=(T, B, 1), sc_lv=(T, B, 1), sh_mean=(T, B, 2), sh_lv=(T, B, 2),
+               g_sh_mean=(T, B, 2), g_sh_lv=(T, B, 2), v_mean=(T, B, Ld), v_lv=(T, B, Ld))
+    st = {k: (torch.randn(v, device=cuda_device, generator=g) * (3.0 if k == "y_pre" else 0.8)).requires_grad_(True) for k, v in shp.items()}
+    st["active_prev"] = torch.rand((T, B), device=cuda_device, generator=g) < 0.7
+    st["active"] = torch.rand((T, B), device=cuda_device, generator=g) < 0.6
+    gk = torch.randn(B, device=cuda_device, generator=g)
+    kl, comps = fused.kl_terms(st, cfg.z_pres_temperature, cfg.scale_prior_mean, cfg.scale_prior_variance, cfg.vae_prior_mean, cfg.vae_prior_variance)
+    (kl * gk).sum().backward()
+    s64 = {k: (v.detach().double().requires_grad_(True) if v.dtype != torch.bool else v) for k, v in st.items()}
+    z_kl = model._concrete_kl(s64["y_pre"], s64["prior_lo"], s64["post_lo"], cfg.z_pres_temperature)
+    sck, shk, vk = model._gaussian_kls(s64["sc_mean"], s64["sc_lv"], s64["sh_mean"], s64["sh_lv"], s64["g_sh_mean"], s64["g_sh_lv"],
+                                       s64["v_mean"], s64["v_lv"])
+    zero = torch.zeros_like(z_kl)
+    parts = [torch.where(s64["active_prev"], z_kl, zero).sum(0)] + [torch.where(s64["active"], t, zero).sum(0) for t in (sck, shk, vk)]
+    ref = sum(parts)
+    (ref * gk.double()).sum().backward()
+    _check(kl, ref, rtol=2e-5, atol=1e-4)
+    for i, p_ in enumerate(parts):
+        _check(comps[:, i], p_, rtol=2e-5, atol=1e-4)
+    for k in shp:
+        _check(st[k].grad, s64[k].grad, rtol=2e-5, atol=1e-5)
