@@ -189,7 +189,7 @@ class _StepAffine:
             DY = torch.cat([dy.detach() for _, dy in self._stash], 0)
             weight_grad_in_out.addmm_(X.t(), DY)
             if bias_from_stash and bias_grad is not None:
-                bias_grad.add_(DY.sum(0))
+                bias_grad.addmv_(DY.t(), DY.new_ones(DY.shape[0]))      # column sums, accumulated in place
         self._stash.clear()
 
 
@@ -361,9 +361,9 @@ class AIRModel(nn.Module):
         inf_state, gen_state = (z(B, H), z(B, H)), (z(B, H), z(B, H))
         gen_prev_out, prev_latent, prev_ss = z(B, H), z(B, L), z(B, 3)
         canvas = z(B, cs, cs)
-        digits = torch.zeros(B, dtype=torch.int32, device=dev)
         kl = {k: [] for k in ("z_pres_kl", "scale_kl", "shift_kl", "vae_kl")}
         hist = {}
+        act_list = []
         lo_list, sh_list, sc_list = [], [], []
         images4 = images.reshape(B, cs, cs, 1)
         # the image block of the inference LSTM input is the same at every step: its 2500x1024 GEMM runs once
@@ -400,7 +400,7 @@ class AIRModel(nn.Module):
             post_lo = self.z_post(F.relu(self.z_post_h(out)))[:, 0]                                         # :620-623
             y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
                                                                           temp, thr)     # concrete.py:20-27, :631, :698-712
-            digits = digits + active.to(torch.int32)                                                        # :715-716
+            act_list.append(active)
             canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
 
             if cfg.stacked_kl:
@@ -420,6 +420,7 @@ class AIRModel(nn.Module):
             step += 1
 
         T = step
+        digits = torch.stack(act_list, 0).sum(0, dtype=torch.int32)                                         # :715-716
         if cfg.stacked_kl:
             H_ = {k: torch.stack(v, 0) for k, v in hist.items()}                                            # [T, B, ...]
             fused_kl = self.ops.kl_terms(H_, cfg) if hasattr(self.ops, "kl_terms") else None

@@ -44,6 +44,7 @@ class Trainer:
         self.t = 0
         self.t_dev = torch.zeros((), dtype=torch.float64, device=self.device)
         self.graph = None
+        self._noise_bank = {}
         self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-8   # tf.train.AdamOptimizer defaults
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed + 1 + (dist.get_rank(process_group) if process_group is not None else 0))
@@ -51,10 +52,15 @@ class Trainer:
     def num_gradient_floats(self) -> int:
         return self.flat_grad.numel()
 
-    def _noise(self, kind, step, shape):
-        if kind == "concrete":
-            return torch.rand(shape, device=self.device, generator=self.gen)
-        return torch.randn(shape, device=self.device, generator=self.gen)
+    def _noise(self, kind, step, shape, generator="own"):
+        """All loop iterations' draws of one kind come from a single RNG launch per training step."""
+        bank = self._noise_bank
+        if kind not in bank:
+            full = (self.cfg.max_steps,) + tuple(shape)
+            gen = self.gen if generator == "own" else None
+            bank[kind] = (torch.rand(full, device=self.device, generator=gen) if kind == "concrete"
+                          else torch.randn(full, device=self.device, generator=gen))
+        return bank[kind][step]
 
     def _any_reduce(self, flag):
         if self.pg is None:
@@ -67,6 +73,7 @@ class Trainer:
         B = images.shape[0]
         nglobal = self.global_batch if self.global_batch is not None else B * self.world
         self.flat_grad.zero_()
+        self._noise_bank = {}
         self.model.set_deferred_weight_grads(self.defer_weight_grads)
         out = self.model(images, noise=noise or self._noise, any_reduce=self._any_reduce if self.pg is not None else None,
                          global_batch=nglobal, recon_loss_fn=recon_loss_fn)
@@ -87,10 +94,10 @@ class Trainer:
         torch.nan_to_num_(g, nan=0.0, posinf=0.0, neginf=0.0)
         c = self.cfg.gradient_clipping_norm
         if c is not None:
-            norms = torch._foreach_norm(self.grads)
-            # tf.clip_by_norm: g * clip / max(norm, clip)
-            scales = [c / torch.clamp(n, min=c) for n in norms]
-            torch._foreach_mul_(self.grads, scales)
+            # tf.clip_by_norm per variable: g * clip / max(norm, clip)  -- all 50 scales in three small kernels
+            norms = torch.stack(torch._foreach_norm(self.grads))
+            scales = c / torch.clamp(norms, min=c)
+            torch._foreach_mul_(self.grads, list(scales.unbind(0)))
         self.t += 1
         b1, b2 = self.beta1, self.beta2
         self.t_dev += 1.0
@@ -113,8 +120,7 @@ class Trainer:
             raise ValueError("graph capture needs AIRConfig.always_max_steps=True")
         cs2 = self.cfg.canvas_size ** 2
         self.static_images = torch.zeros((batch_size, cs2), device=self.device)
-        noise = lambda kind, step, shape: (torch.rand(shape, device=self.device) if kind == "concrete"
-                                           else torch.randn(shape, device=self.device))
+        noise = lambda kind, step, shape: self._noise(kind, step, shape, generator="default")   # graph-safe default generator
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
