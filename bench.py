@@ -446,7 +446,44 @@ def aux_section(dev):
                           bytes_per_pixel=8, shape=[Bc, P])
     out["bce_bwd"] = dict(us=t_b, gbs=12.0 * Bc * P / (t_b * 1e-6) / 1e9, frac=12.0 * Bc * P / (t_b * 1e-6) / 1e9 / peak,
                           bytes_per_pixel=12, shape=[Bc, P])
+    out["detection"] = detection_section(dev, timeit)
     return out
+
+
+def detection_section(dev, timeit):
+    """Detection metrics (evaluation_detection.py:29-98) for a 10 000-image evaluation set, 3 ground-truth and up to 3
+    inferred boxes: the kernel alone, the reference-signature call (ragged host lists in, means out) and the CPU port
+    of the reference loop on a 2 000-image sample (cpu_baseline leg: the only place the oracle is timed)."""
+    import numpy as np
+    import torch
+    from mog_asr_b200 import detection
+    rng = np.random.default_rng(0)
+    n, cs, G, T = 10000, 50, 3, 3
+    gt_num, inf_num = rng.integers(0, G + 1, n), rng.integers(0, T + 1, n)
+    wh = rng.integers(8, 24, (n, G, 2))
+    xy = (rng.random((n, G, 2)) * (cs - wh)).astype(np.int64)
+    pos = [xy[k, :gt_num[k]].reshape(-1).tolist() for k in range(n)]
+    size = [wh[k, :gt_num[k]].reshape(-1).tolist() for k in range(n)]
+    shifts = np.tanh(rng.normal(0, 0.5, (n, T, 2))).astype(np.float32)
+    scales = (1 / (1 + np.exp(-rng.normal(-1, 0.5, (n, T, 1))))).astype(np.float32)
+    d = lambda a: torch.as_tensor(a).to(dev)
+    P, S, num = detection.pack_ground_truth(pos, size)
+    dP, dS, dnum, dsh, dsc, dinf = d(P), d(S), d(num), d(shifts).double(), d(scales).double(), d(inf_num.astype(np.int32))
+    t_kernel = timeit(lambda: detection.detection_metrics(dP, dS, dnum, dsh, dsc, dinf, cs), 50)
+    t0 = time.perf_counter()
+    got = detection.evaluation(pos, size, shifts, scales, inf_num, csize=cs, device=dev)
+    t_call = time.perf_counter() - t0
+    from oracle import detection_ref                       # CPU baseline leg
+    m = 2000
+    t0 = time.perf_counter()
+    want = detection_ref.evaluation(pos[:m], size[:m], shifts[:m], scales[:m], inf_num[:m], csize=cs)
+    t_cpu = time.perf_counter() - t0
+    chk = detection.evaluation(pos[:m], size[:m], shifts[:m], scales[:m], inf_num[:m], csize=cs, device=dev)
+    same = all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(chk[:4], want[:4])) and abs(chk[4] - want[4]) < 1e-14
+    return dict(images=n, kernel_us=t_kernel, images_per_s_kernel=n / (t_kernel * 1e-6), call_ms_host_lists=t_call * 1e3,
+                images_per_s_call=n / t_call, precision_at_0p5=float(got[0][0]),
+                cpu_baseline=dict(value=m / t_cpu, unit="images/s", cores=1, kind="port", sample=f"{m} images, oracle/detection_ref.py"),
+                matches_cpu_port=bool(same))
 
 
 def train_section(a, dev, world, pg, rank):

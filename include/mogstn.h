@@ -181,6 +181,18 @@ MOG_API int mog_air_kl_backward(const float* y_pre, const float* prior_lo, const
                         float* d_sh_mean, float* d_sh_lv, float* d_g_sh_mean, float* d_g_sh_lv, float* d_v_mean,
                         float* d_v_lv, void* stream);
 
+/* ---- detection metrics of the evaluation pass ------------------------------------------------------------
+ * air/evaluation_detection.py:29-98 for a whole batch in one launch.  gt_pos / gt_size: [B][G][2] int32 (x, y) and (w, h)
+ * of each ground-truth box, the first gt_num[b] valid; inf_shifts [B][T][2], inf_scales [B][T] float64 (the model's
+ * fp32 outputs widened, as numpy does), the first inf_num[b] valid; G, T <= MOG_DET_MAX_BOXES; counts are clamped to
+ * G / T.  Outputs per image: precision, recall [B][11] (thresholds 0.5 + 0.05 i, strict >), gt_max_iou,
+ * detected_max_iou, global_iou [B] (matched IoU sum / max(#gt, #inferred)); the reference returns their batch means. */
+#define MOG_DET_MAX_BOXES 8
+MOG_API int mog_detection_eval(const int* gt_pos, const int* gt_size, const int* gt_num, const double* inf_shifts,
+                       const double* inf_scales, const int* inf_num, int64_t B, int G, int T, double csize,
+                       double* precision, double* recall, double* gt_max_iou, double* detected_max_iou,
+                       double* global_iou, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@ from .transformer import transformer, batch_transformer, stn_corners  # noqa: F4
 from .composite import write_composite  # noqa: F401
 from .asr import AsrRegulariser, asr_regularisers  # noqa: F401
 from .recon import reconstruction_loss  # noqa: F401
+from . import detection  # noqa: F401
 
 __all__ = ["transformer", "batch_transformer", "stn_corners", "write_composite", "AsrRegulariser",
-           "asr_regularisers", "reconstruction_loss"]
+           "asr_regularisers", "reconstruction_loss", "detection"]
