@@ -40,6 +40,9 @@ int sm_count() {
     return cached[dev];
 }
 
+#ifndef MOG_BULK_ZERO
+#define MOG_BULK_ZERO 1   // large zero regions go to the bulk-copy engine (0: ordinary stores; A/B experiments)
+#endif
 #ifndef MOG_COOP_ZERO_MIN_FLOATS
 #define MOG_COOP_ZERO_MIN_FLOATS 8192   // dU images of >= 32 KB are zero-filled by the whole CTA
 #endif
@@ -123,8 +126,9 @@ static int set_smem(K kernel, size_t bytes) {
 template <bool COMPOSITE>
 static int launch_fwd(FwdArgs a, cudaStream_t st) {
     if (a.B == 0) return MOG_OK;
-    const size_t smem = (size_t)kWarpsPerCta * a.g.Ho * sizeof(int4);
-    MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d too large for the per-warp row tables", a.g.Ho);
+    a.bulk_zero = (!COMPOSITE && MOG_BULK_ZERO && (long long)a.g.N * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS) ? 1 : 0;
+    const size_t smem = (size_t)kWarpsPerCta * (a.g.Ho + a.g.Wo) * sizeof(int4) + (a.bulk_zero ? kZeroBytes : 0);
+    MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d too large for the per-warp tables", a.g.Ho, a.g.Wo);
     if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
     const long long ctas = (a.B + kWarpsPerCta - 1) / kWarpsPerCta;
     stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, MOG_FWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
@@ -134,7 +138,7 @@ static int launch_fwd(FwdArgs a, cudaStream_t st) {
 
 template <bool COMPOSITE, int NXC>
 static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)kWarpsPerCta * bwd_warp_smem_words(a.g) * sizeof(int);
+    const size_t smem = (size_t)kWarpsPerCta * bwd_warp_smem_words(a.g) * sizeof(int) + (a.coop_zero == 2 ? kZeroBytes : 0);
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d Ws=%d too large for the per-warp tables",
                 a.g.Ho, a.g.Wo, a.g.Ws);
     if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC>, smem)) return rc;
@@ -148,6 +152,7 @@ template <bool COMPOSITE>
 static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
+    if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
     const int nxc = (a.g.Ws + 31) / 32;
     if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);

@@ -274,3 +274,32 @@ def test_host_buffer_entry_point_matches_device_path(cuda_device):
     assert torch.equal(out, o.detach().cpu()) and torch.equal(dU, Ud.grad.cpu()) and torch.equal(dth, td.grad.cpu())
     out2, dU2, dth2 = hs.fwd_bwd(U, th, g, need_dU=False)
     assert dU2 is None and torch.equal(out2, out) and torch.equal(dth2, dth)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src,dst", [((131, 127), (33, 29)), ((33, 29), (131, 127)), ((256, 256), (64, 64)), ((64, 64), (256, 256)),
+                                     ((90, 93), (90, 93))])
+def test_large_images_every_element_written(cuda_device, src, dst):
+    """Large outputs / source gradients are mostly zeros written by the bulk-copy engine (rows outside the footprint)
+    and by ordinary stores (the footprint band): poison the allocator's blocks first so that an element nobody wrote
+    shows up as NaN; odd widths put every image at a different 16-byte misalignment."""
+    B = 9
+    rng = np.random.default_rng(src[0] * 7 + dst[1])
+    s, x, y = synth.sxy_prior_like(B, seed=5)
+    s[0], x[0], y[0] = 0.05, 0.97, -0.97          # footprint hanging over a corner
+    s[1], x[1], y[1] = 1.7, 0.0, 0.0              # covers everything
+    th = synth.theta_read(s, x, y) if src[0] >= dst[0] else synth.theta_write(s, x, y)
+    th[2] = [0.5, 0, 5.0, 0, 0.5, 5.0]            # entirely out of range: no footprint at all
+    U = rng.random((B, src[0], src[1], 1), dtype=np.float32)
+    g = rng.normal(size=(B, dst[0], dst[1], 1)).astype(np.float32)
+    for n in (B * src[0] * src[1], B * dst[0] * dst[1]):
+        poison = torch.full((n,), float("nan"), device=cuda_device)
+        del poison
+    out, dU, dth = run_fwd_bwd(cuda_device, U, th, dst, g)
+    ref_out = RC.forward(U, th, dst)
+    assert H.same_bits_or_nan(out, ref_out)
+    dU64, dth64 = R.transformer_backward(U, th, dst, g, dtype=np.float64)
+    aU, ath = R.backward_term_magnitudes(U, th, dst, g)
+    assert np.isfinite(dU).all()
+    assert H.grad_excess(dU, dU64, aU) <= 1.0
+    assert H.grad_excess(dth, dth64, ath) <= 1.0
