@@ -492,6 +492,11 @@ def train_section(a, dev, world, pg, rank):
     out = {}
     r = bench_train.run("C4", dev, steps=10, warmup=3, process_group=pg, always_max_steps=True, graph=True)
     out["C4_global4096"] = r
+    if world > 1:
+        # the same model with the per-GPU work held at 4096 images (weak scaling): separates the all-reduce cost from
+        # the fixed per-step launch chain that bounds the strong-scaling line above
+        out["C4_weak_4096_per_gpu"] = bench_train.run("C4", dev, steps=10, warmup=3, process_group=pg, always_max_steps=True,
+                                                      graph=True, per_rank_batch=4096)
     if world == 1:
         for name in ("C2", "C3"):
             out[name + "_graph"] = bench_train.run(name, dev, steps=10, warmup=3, always_max_steps=True, graph=True)

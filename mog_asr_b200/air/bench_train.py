@@ -24,11 +24,14 @@ def synthetic_batch(cfg, batch, seed, device):
     return torch.tensor(np.clip(canv, 0.0, 1.0).reshape(batch, -1), device=device)
 
 
-def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=False, graph=False):
-    """Returns dict(images_per_sec, ms_per_step, global_batch, per_rank_batch, mean loop steps)."""
+def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=False, graph=False, per_rank_batch=None):
+    """Returns dict(images_per_sec, ms_per_step, global_batch, per_rank_batch, mean loop steps).  ``per_rank_batch``
+    overrides the config's fixed global batch with ``per_rank_batch * world`` (weak scaling)."""
     flags, gbatch = CONFIGS[name]
     world = dist.get_world_size(process_group) if process_group is not None else 1
     rank = dist.get_rank(process_group) if process_group is not None else 0
+    if per_rank_batch is not None:
+        gbatch = per_rank_batch * world
     cfg = config_from_flags(always_max_steps=always_max_steps, **flags)
     local = gbatch // world
     tr = Trainer(cfg, device, process_group=process_group, global_batch=gbatch)

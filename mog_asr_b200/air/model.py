@@ -59,6 +59,10 @@ class AIRConfig:
     always_max_steps: bool = False               # run max_steps iterations regardless of the `any` test (:386-390)
     stacked_kl: bool = True                      # evaluate the four KL terms once on [T,B,..] stacks after the loop
                                                  # (same elementwise math as the per-step form, 6x fewer launches)
+    batched_tail: bool = True                    # with always_max_steps: everything that does not feed the next
+                                                 # step's inference input (generative LSTM and prior heads, z_pres
+                                                 # heads, VAE decoder, canvas writes) runs after the loop, the
+                                                 # non-recurrent layers once over all T*B rows
 
 
 def config_from_flags(data="mnist", dn="13", ds="", gn=0.0, gm=0.0, gne=0.0, gb=0.0, gs=0.0, ga=0.0, zt=0.1, **kw):
@@ -234,10 +238,11 @@ class LSTMCellTF(nn.Module, _StepAffine):
         once per loop iteration -- the same sum, associated differently -- and ``x`` then holds only the rest."""
         c, h = state
         self._static_width = static_width if static_gates is not None else 0
+        xh = h if x.shape[1] == 0 else torch.cat([x, h], 1)
         if static_gates is None:
-            gates = self._affine(torch.cat([x, h], 1), self.kernel, self.bias)
+            gates = self._affine(xh, self.kernel, self.bias)
         else:
-            gates = self._affine(torch.cat([x, h], 1), self.kernel[static_width:], self.bias, base=static_gates)
+            gates = self._affine(xh, self.kernel[static_width:], self.bias, base=static_gates)
         if pointwise is not None:
             c2, h2 = pointwise(gates, c)
         else:
@@ -357,6 +362,8 @@ class AIRModel(nn.Module):
                                                else torch.randn(shape, device=dev, dtype=dt))
         H, L = cfg.rnn_units, cfg.vae_latent_dimensions
         z = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+        if cfg.always_max_steps and cfg.batched_tail and cfg.stacked_kl:
+            return self._forward_batched_tail(images, noise, global_batch, recon_loss_fn)
         stop_sum = z(B)
         inf_state, gen_state = (z(B, H), z(B, H)), (z(B, H), z(B, H))
         gen_prev_out, prev_latent, prev_ss = z(B, H), z(B, L), z(B, 3)
@@ -390,14 +397,14 @@ class AIRModel(nn.Module):
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
 
             theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)                                        # :511-531,:563-584
-            window = self.ops.transformer(images4, theta_r, (ws, ws))[:, :, :, 0]                           # :534-542
+            window = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws, ws)                      # :534-542
             recon, v_mean, v_lv, v_latent = self._vae(window.reshape(B, ws * ws), noise("vae", step, (B, L)))  # :544-553
 
             if cfg.fix_steps is not None:                                                                   # :604-608
                 prior_lo = torch.full((B,), 100.0 if step < cfg.fix_steps else -100.0, device=dev, dtype=dt)
             else:
-                prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev_out)))[:, 0]                         # :609-615
-            post_lo = self.z_post(F.relu(self.z_post_h(out)))[:, 0]                                         # :620-623
+                prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev_out))).reshape(B)                     # :609-615
+            post_lo = self.z_post(F.relu(self.z_post_h(out))).reshape(B)                                     # :620-623
             y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
                                                                           temp, thr)     # concrete.py:20-27, :631, :698-712
             act_list.append(active)
@@ -419,10 +426,99 @@ class AIRModel(nn.Module):
             gen_prev_out, prev_latent, prev_ss = gen_out, v_latent, ss_latent
             step += 1
 
-        T = step
+        H_ = {k: torch.stack(v, 0) for k, v in hist.items()} if cfg.stacked_kl else None                   # [T, B, ...]
+        return self._epilogue(images, canvas, act_list, H_, kl, torch.stack(lo_list, 1), torch.stack(sh_list, 1),
+                              torch.stack(sc_list, 1), step, global_batch, recon_loss_fn)
+
+    def _forward_batched_tail(self, images, noise, global_batch, recon_loss_fn):
+        """Same graph as the loop in ``forward`` with a fixed trip count, evaluated in dependency order rather than
+        in program order.  The next step's inference input is ``[image, previous VAE latent, previous shift/scale]``
+        (:413-422), so only the inference LSTM, the shift/scale heads, the glimpse read and the VAE encoder are truly
+        sequential.  The generative LSTM (:465-470) is a chain of its own; its input half, its prior heads
+        (:472-481, :609-615), the z_pres heads (:620-623) and the VAE decoder (vae.py:34-41) have no recurrence at
+        all and run once over all ``T*B`` rows; the Concrete / stopping-sum scan and the canvas writes follow in
+        step order.  Same sums, same noise per (kind, step); GEMMs see ``T*B`` rows instead of ``B``."""
+        cfg = self.cfg
+        dev, dt = images.device, images.dtype
+        B, T = images.shape[0], cfg.max_steps
+        cs, ws, thr, temp = cfg.canvas_size, cfg.windows_size, cfg.stopping_threshold, cfg.z_pres_temperature
+        H, L = cfg.rnn_units, cfg.vae_latent_dimensions
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+        lstm_pw = getattr(self.ops, "lstm_pointwise", None)
+        images4 = images.reshape(B, cs, cs, 1)
+        img_gates, img_w = self.infer_cell.static_part(images)
+
+        # ---- the recurrence proper -------------------------------------------------------------------------
+        inf_state = (z(B, H), z(B, H))
+        prev_latent, prev_ss = z(B, L), z(B, 3)
+        per = {k: [] for k in ("out", "prev", "latent", "theta_w", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "v_mean", "v_lv",
+                               "shift", "scale")}
+        for step in range(T):
+            prev = torch.cat([prev_latent, prev_ss], -1)
+            out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w, pointwise=lstm_pw)
+            sh_mean, sh_lv = self.inf_shift(out)
+            shift_latent, inf_shift = self.ops.gauss_sample(sh_mean, sh_lv, noise("shift", step, (B, 2)), "tanh")
+            sc_mean, sc_lv = self.inf_scale(out, shift_latent)
+            scale_latent, inf_scale = self.ops.gauss_sample(sc_mean, sc_lv, noise("scale", step, (B, 1)), "sigmoid")
+            theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)
+            x = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws * ws)   # C = 1: a view, no select
+            for l in self.vae_rec:
+                x = F.softplus(l(x))
+            v_mean, v_lv = self.vae_rec_mean(x), self.vae_rec_logvar(x)
+            v_latent, _ = self.ops.gauss_sample(v_mean, v_lv, noise("vae", step, (B, L)))
+            for k, v in (("out", out), ("prev", prev), ("latent", v_latent), ("theta_w", theta_w), ("sc_mean", sc_mean),
+                         ("sc_lv", sc_lv), ("sh_mean", sh_mean), ("sh_lv", sh_lv), ("v_mean", v_mean), ("v_lv", v_lv),
+                         ("shift", inf_shift), ("scale", inf_scale)):
+                per[k].append(v)
+            prev_latent, prev_ss = v_latent, torch.cat([shift_latent, scale_latent], -1)
+
+        # ---- generative LSTM: input half for all steps at once, then its own chain ---------------------------
+        gen_static, gen_w = self.gen_cell.static_part(torch.cat(per["prev"], 0))
+        gen_static = gen_static.reshape(T, B, 4 * H).unbind(0)   # (unbind, not [step]: one stack in the backward pass
+        gen_state, gen_outs, none = (z(B, H), z(B, H)), [], z(B, 0)  #  instead of T zero-filled scatters that are then added)
+        for step in range(T):
+            g_out, gen_state = self.gen_cell(none, gen_state, static_gates=gen_static[step], static_width=gen_w, pointwise=lstm_pw)
+            gen_outs.append(g_out)
+        g_sh_mean, g_sh_lv = self.gen_shift(torch.cat(gen_outs, 0))                                            # :472-481
+        if cfg.fix_steps is not None:                                                                        # :604-608
+            prior_lo = torch.full((T, B), -100.0, device=dev, dtype=dt)
+            prior_lo[:cfg.fix_steps] = 100.0
+        else:
+            gen_prev = torch.cat([z(B, H)] + gen_outs[:-1], 0)
+            prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev))).reshape(T, B)                    # :609-615
+        post_lo = self.z_post(F.relu(self.z_post_h(torch.cat(per["out"], 0)))).reshape(T, B)            # :620-623
+
+        # ---- VAE decoder for all steps (vae.py:34-41) ----------------------------------------------------------
+        x = torch.cat(per["latent"], 0)
+        for l in self.vae_gen:
+            x = F.softplus(l(x))
+        recon = torch.sigmoid(self.vae_gen_mean(x)).reshape(T, B, ws, ws).unbind(0)
+
+        # ---- Concrete / stopping-sum scan and the canvas writes, in step order -----------------------------------
+        stop_sum, canvas = z(B), z(B, cs, cs)
+        y_pre_l, act_prev_l, act_l = [], [], []
+        post_lo_t = post_lo.unbind(0)
+        for step in range(T):
+            y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo_t[step], noise("concrete", step, (B,)), stop_sum,
+                                                                          temp, thr)
+            canvas = self.ops.write_composite(canvas, recon[step], per["theta_w"][step], z_pres, stop_sum, thr)
+            y_pre_l.append(y_pre); act_prev_l.append(active_prev); act_l.append(active)
+
+        st = lambda k: torch.stack(per[k], 0)
+        H_ = dict(y_pre=torch.stack(y_pre_l, 0), prior_lo=prior_lo, post_lo=post_lo, active_prev=torch.stack(act_prev_l, 0),
+                  active=torch.stack(act_l, 0), sc_mean=st("sc_mean"), sc_lv=st("sc_lv"), sh_mean=st("sh_mean"), sh_lv=st("sh_lv"),
+                  g_sh_mean=g_sh_mean.reshape(T, B, 2), g_sh_lv=g_sh_lv.reshape(T, B, 2), v_mean=st("v_mean"), v_lv=st("v_lv"))
+        return self._epilogue(images, canvas, act_l, H_, None, post_lo.t().contiguous(), torch.stack(per["shift"], 1),
+                              torch.stack(per["scale"], 1), T, global_batch, recon_loss_fn)
+
+    def _epilogue(self, images, canvas, act_list, H_, kl, log_odds, shifts, scales, T, global_batch, recon_loss_fn):
+        """everything after the loop: object counts, KL terms (:690-787,:930-935), reconstruction loss (:945-968),
+        ASR regularisers (:645-681,:970-1069) and the loss (:1078-1079)"""
+        cfg = self.cfg
+        B = images.shape[0]
+        cs, temp = cfg.canvas_size, cfg.z_pres_temperature
         digits = torch.stack(act_list, 0).sum(0, dtype=torch.int32)                                         # :715-716
         if cfg.stacked_kl:
-            H_ = {k: torch.stack(v, 0) for k, v in hist.items()}                                            # [T, B, ...]
             fused_kl = self.ops.kl_terms(H_, cfg) if hasattr(self.ops, "kl_terms") else None
         if cfg.stacked_kl and fused_kl is not None:
             elbo = fused_kl                                                                                 # :690-787,:930-935 fused
@@ -442,8 +538,6 @@ class AIRModel(nn.Module):
         else:
             rec_loss = recon_loss_fn(images, torch.clamp(canvas2, 0.0, 1.0))
         elbo = elbo + rec_loss                                                                              # :968
-        log_odds = torch.stack(lo_list, 1)
-        shifts, scales = torch.stack(sh_list, 1), torch.stack(sc_list, 1)
         per_image, margin, comps = self.ops.asr(cfg, log_odds, shifts, scales)                              # :645-681,:970-1069
         nglobal = B if global_batch is None else global_batch
         # loss = mean_b(elbo + pr_loss + num_element_min) + num_marginal_loss  (:1078-1079); under data

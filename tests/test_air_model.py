@@ -74,6 +74,32 @@ def test_stacked_kl_equals_per_step_form(flags):
     assert float((g1[fin] - g0[fin]).abs().max()) <= 1e-5 * float(g0[fin].abs().max())
 
 
+@pytest.mark.parametrize("flags,defer", [(dict(data="mnist", dn="13", gm=100.0, gne=10.0), True),
+                                         (dict(data="sprites", dn="3", ds="bbox20k", gb=1.0, gs=10.0, ga=20.0), False)])
+def test_batched_tail_equals_loop_form(flags, defer):
+    """Dependency-ordered evaluation (generative LSTM, prior / z_pres heads, VAE decoder and canvas writes after the
+    inference recurrence, the non-recurrent layers once over all T*B rows) against the step-by-step loop of the
+    reference (:393-727) with the same fixed trip count: same loss, same per-image ELBO, same gradients (only GEMM
+    row-batching and summation order over steps differ).  -dn 13 has learned z_pres priors, -dn 3 the fixed ones."""
+    images, _ = make_images(6, 50 if flags["data"] == "mnist" else 64, seed=2)
+    res = []
+    for tail in (False, True):   # float64: in fp32 the reference cross-entropy (1e10 slopes at canvas == 0) amplifies the
+        cfg = config_from_flags(always_max_steps=True, batched_tail=tail, **flags)      # GEMM re-batching noise to 4e-4
+        tr = Trainer(cfg, "cpu", ops=OracleOps(), seed=5, defer_weight_grads=defer, dtype=torch.float64)
+        out = tr.forward_backward(images.double(), noise=SeededNoise(4, 6, dtype=torch.float64))
+        res.append((float(out["loss"].detach()), out["elbo"].clone(), tr.flat_grad.clone(), out["steps"], out["rec_num_digits"].clone(),
+                    out["reconstruction"].clone()))
+    (l0, e0, g0, t0, d0, r0), (l1, e1, g1, t1, d1, r1) = res
+    assert t0 == t1 and torch.equal(d0, d1)
+    np.testing.assert_allclose(l1, l0, rtol=1e-8)
+    assert torch.allclose(e1, e0, rtol=1e-8, atol=1e-4)
+    assert torch.allclose(r1, r0, atol=1e-6)
+    fin = torch.isfinite(g0)
+    assert torch.equal(torch.isfinite(g1), fin)
+    assert float((g1[fin] - g0[fin]).abs().max()) <= 1e-4 * float(g0[fin].abs().max())   # the sampler itself stays fp32
+    assert float(g0[fin].abs().max()) > 0
+
+
 def test_deferred_weight_gradients_equal_autograd():
     """One GEMM per layer over the concatenated rows of all loop iterations == per-iteration autograd accumulation."""
     cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0)

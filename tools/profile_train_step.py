@@ -19,7 +19,7 @@ for e in ev:
     a = agg[e.name[:70]]; a[0] += 1; a[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
 tot = sum(v[1] for v in agg.values()); n = sum(v[0] for v in agg.values())
 print(f"batch {B}: {n} kernels, {tot/1e3:.2f} ms of GPU time")
-for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:80]:
     print(f"{c:5d} {t/1e3:8.3f} ms {100*t/tot:5.1f}%  {k}")
 ops = collections.Counter()
 for e in prof.events():
