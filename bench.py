@@ -302,8 +302,8 @@ def e2e_measure(a, dev, steps, warmup):
         th_r.append(torch.from_numpy(synth.theta_read(s, x, y)).pin_memory())
         th_w.append(torch.from_numpy(synth.theta_write(s, x, y)).pin_memory())
     out_r, dU_r, out_w, dU_w, dth = pin(B, gs, gs, 1), pin(B, cs, cs, 1), pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, 6)
-    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(256, min(2048, B // 8)))
-    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=max(256, min(2048, B // 8)))
+    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(256, min(512, B // 8)))
+    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=max(256, min(512, B // 8)))
 
     def step():
         for t in range(AIR_STEPS):
