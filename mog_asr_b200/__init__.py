@@ -10,6 +10,7 @@ from .composite import write_composite  # noqa: F401
 from .asr import AsrRegulariser, asr_regularisers  # noqa: F401
 from .recon import reconstruction_loss  # noqa: F401
 from . import detection  # noqa: F401
+from .visualize import attention_boxes  # noqa: F401
 
 __all__ = ["transformer", "batch_transformer", "stn_corners", "write_composite", "AsrRegulariser",
-           "asr_regularisers", "reconstruction_loss", "detection"]
+           "asr_regularisers", "reconstruction_loss", "detection", "attention_boxes"]

@@ -303,3 +303,20 @@ def test_large_images_every_element_written(cuda_device, src, dst):
     assert np.isfinite(dU).all()
     assert H.grad_excess(dU, dU64, aU) <= 1.0
     assert H.grad_excess(dth, dth64, ath) <= 1.0
+
+
+def test_attention_boxes_match_oracle(cuda_device):
+    """Visualisation consumer (air_number_bbox_location.py:243-288): frame template written through the backward ST
+    matrices at 2x canvas resolution, clipped and thresholded; one shared template vs the oracle's physical copies."""
+    n, steps, T, cs, ws, zoom = 5, 2, 3, 50, 28, 2
+    s, x, y = synth.sxy_prior_like(n * steps, seed=8)
+    th = synth.theta_write(s, x, y).reshape(n, steps, 6)
+    got = M.attention_boxes(torch.tensor(th, device=cuda_device), cs, zoom=zoom, windows_size=ws, max_steps=T).cpu().numpy()
+    tmpl = np.zeros((ws, ws, 1), np.float32)
+    tmpl[0], tmpl[-1], tmpl[:, 0], tmpl[:, -1] = 1, 1, 1, 1
+    thp = np.concatenate([th, np.zeros((n, T - steps, 6), np.float32)], 1).reshape(n * T, 6)
+    ref = RC.forward(np.repeat(tmpl[None], n * T, 0), thp, (zoom * cs, zoom * cs))
+    ref = (np.clip(ref, 0, 1) > 0.01).astype(np.float32).reshape(n, T, zoom * cs, zoom * cs)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert 0 < got[:, :steps].mean() < 0.5          # frames, not filled boxes
+    assert np.all(got[:, steps:] == 0.0)            # zero matrices sample the template's centre (= 0) everywhere
