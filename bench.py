@@ -447,7 +447,30 @@ def aux_section(dev):
     out["bce_bwd"] = dict(us=t_b, gbs=12.0 * Bc * P / (t_b * 1e-6) / 1e9, frac=12.0 * Bc * P / (t_b * 1e-6) / 1e9 / peak,
                           bytes_per_pixel=12, shape=[Bc, P])
     out["detection"] = detection_section(dev, timeit)
+    out["dataset"] = dataset_section(dev, timeit)
     return out
+
+
+def dataset_section(dev, timeit):
+    """On-device synthetic feeder (multi_mnist.py:110-221 placement + paste through the sampler): canvases per second
+    for 50x50 Multi-MNIST-like batches of 4096, next to this repo's numpy generator on one host core."""
+    import torch
+    from mog_asr_b200 import synth
+    from mog_asr_b200.dataset import DeviceMultiObjectDataset, default_sprites
+    ds = DeviceMultiObjectDataset(default_sprites(256, 28, seed=0), 50, (1, 2, 3), (17, 23), mode="disjoint", seed=5, device=dev)
+    B = 4096
+    k = [0]
+
+    def gen():
+        k[0] += 1
+        return ds.batch(k[0], B)
+    t_us = timeit(gen, 20)
+    t_place = timeit(lambda: ds.place(0, B), 50)
+    t0 = time.perf_counter()
+    synth.multi_object_canvases(256, 50, 28, (1, 2, 3), seed=0)
+    t_host = (time.perf_counter() - t0) / 256
+    return dict(batch=B, us_per_batch=t_us, canvases_per_s=B / (t_us * 1e-6), placement_kernel_us=t_place,
+                host_numpy_generator_canvases_per_s=1.0 / t_host, host_cores=1)
 
 
 def detection_section(dev, timeit):

@@ -193,6 +193,20 @@ MOG_API int mog_detection_eval(const int* gt_pos, const int* gt_size, const int*
                        double* precision, double* recall, double* gt_max_iou, double* detected_max_iou,
                        double* global_iou, void* stream);
 
+/* ---- synthetic dataset: object placement (the step before the hot path) ------------------------------------
+ * multi_mnist.py:110-221 / multi_dsprites.py:92-302 for a whole batch in one launch: per canvas a count from
+ * counts[0..num_counts) (host array), per object a sprite id in [0, num_sprites), a square size in [size_min, size_max]
+ * pixels (one per canvas when share_size) and a position inside the margins found by <= 100 rejection draws against
+ * the objects already placed; mode 0 = the reference's bounding_boxes_overlap as written (x-intervals only), mode 1 =
+ * true box intersection.  Draws are a counter-based hash of (seed, first_canvas + b, ...): reproducible, independent
+ * of B.  Outputs: num [B], pos / size [B][max_objects][2] (x, y) / (w, h), sprite [B][max_objects] (int32; unused = 0). */
+#define MOG_SYNTH_MAX_OBJECTS 8
+#define MOG_SYNTH_MAX_COUNTS 8
+#define MOG_SYNTH_MAX_RESTARTS 32
+MOG_API int mog_synth_place(uint64_t seed, int64_t first_canvas, int64_t B, int canvas, int max_objects, const int* counts,
+                    int num_counts, int size_min, int size_max, int gap, int margin, int mode, int share_size,
+                    int num_sprites, int* num, int* pos, int* size, int* sprite, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,22 @@ CONFIGS = {
 }
 
 
+_DATASETS = {}
+
+
 def synthetic_batch(cfg, batch, seed, device):
+    """``[batch, canvas*canvas]`` canvases in [0, 1].  On a GPU they come from the on-device feeder
+    (``mog_asr_b200/dataset.py``: placement kernel + the sampler's own write direction); the numpy generator of
+    ``synth.py`` serves the CPU tests."""
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        from ..dataset import DeviceMultiObjectDataset, default_sprites
+        key = (str(dev), cfg.canvas_size, tuple(cfg.constrains_num), tuple(cfg.constrains_area_minmax))
+        if key not in _DATASETS:
+            lo, hi = (int(v) for v in cfg.constrains_area_minmax)
+            _DATASETS[key] = DeviceMultiObjectDataset(default_sprites(256, 28, seed=0), cfg.canvas_size, tuple(cfg.constrains_num),
+                                                      (lo, hi), mode="disjoint", seed=1234, device=dev)
+        return torch.clamp(_DATASETS[key].batch(seed, batch)["images"], 0.0, 1.0)
     canv, _ = synth.multi_object_canvases(batch, cfg.canvas_size, 28, tuple(cfg.constrains_num), seed=seed)
     return torch.tensor(np.clip(canv, 0.0, 1.0).reshape(batch, -1), device=device)
 
