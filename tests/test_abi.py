@@ -53,11 +53,23 @@ def test_bad_arguments_are_rejected_before_any_launch(lib):
     assert lib.mog_asr_reg_forward(one, one, one, None, 1.0, 4, 99, ctypes.byref(cfg), one, None, one, None) == -2
     with pytest.raises(RuntimeError, match="bad argument"):
         _lib.check(lib.mog_stn_forward(one, one, one, 4, 0, 50, 1, 28, 28, 1, None), "mog_stn_forward")
+    # the rows built around the sampler validate the same way
+    assert lib.mog_detection_eval(one, one, one, one, one, one, 4, 9, 3, 50.0, one, one, one, one, one, None) == -2   # > 8 boxes
+    assert "max 8 boxes" in _lib.last_error()
+    assert lib.mog_detection_eval(one, one, None, one, one, one, 4, 3, 3, 50.0, one, one, one, one, one, None) == -1
+    counts = (ctypes.c_int * 2)(1, 3)
+    assert lib.mog_synth_place(1, 0, 4, 50, 3, counts, 2, 17, 23, 0, 0, 2, 0, 8, one, one, one, one, None) == -2      # mode 2
+    assert lib.mog_synth_place(1, 0, 4, 50, 2, counts, 2, 17, 23, 0, 0, 0, 0, 8, one, one, one, one, None) == -2      # count 3 > max_objects 2
+    assert "exceeds max_objects" in _lib.last_error()
+    assert lib.mog_synth_place(1, 0, 4, 50, 3, counts, 2, 17, 23, 0, 0, 0, 0, 8, None, one, one, one, None) == -1
+    assert lib.mog_bce_recon_forward(one, one, one, None, 4, 0, None) == -2
 
 
 def test_zero_batch_is_a_no_op(lib):
     assert lib.mog_stn_forward(None, None, None, 0, 50, 50, 1, 28, 28, 1, None) == 0
     assert lib.mog_stn_backward(None, None, None, None, None, 0, 50, 50, 1, 28, 28, 1, None) == 0
+    assert lib.mog_detection_eval(None, None, None, None, None, None, 0, 3, 3, 50.0, None, None, None, None, None, None) == 0
+    assert lib.mog_synth_place(1, 0, 0, 50, 3, (ctypes.c_int * 1)(1), 1, 17, 23, 0, 0, 0, 0, 8, None, None, None, None, None) == 0
 
 
 def test_host_wrappers_refuse_cpu_tensors():
