@@ -207,6 +207,25 @@ MOG_API int mog_synth_place(uint64_t seed, int64_t first_canvas, int64_t B, int 
                     int num_counts, int size_min, int size_max, int gap, int margin, int mode, int share_size,
                     int num_sprites, int* num, int* pos, int* size, int* sprite, void* stream);
 
+/* ---- two-layer (mean, log-variance) heads of the loop body, fused after the first GEMM ---------------------------------
+ * air_number_bbox_location.py:424-460, :472-481.  pre1 [B][2h] = x [W1m | W1v] (first-layer GEMM without bias, computed by
+ * the caller); weights in the nn.Linear layout: w1m / w1v [h][K+S] (only the S skip columns at K.. are read), b1* [h],
+ * w2m / w2v [O][h+S], b2* [O]; skip [B][S] (S = 0: none), eps [B][O]; act as for gauss_sample.  hidden in {16,32,64,128}.
+ * forward: mean, logvar, latent [B][O] (+ squashed when act != 0).
+ * backward: g_* nullable gradients of the four outputs; dpre1 [B][2h] and dskip [B][S] are fully overwritten; the
+ * second-layer parameter gradients gw2m / gw2v [O][h+S], gb2m / gb2v [O] are ACCUMULATED (atomics) into the given buffers. */
+#define MOG_HEAD_MAX_SKIP 2
+#define MOG_HEAD_MAX_OUT 2
+MOG_API int mog_air_head_forward(const float* pre1, const float* skip, const float* eps, const float* w1m, const float* b1m,
+                         const float* w1v, const float* b1v, const float* w2m, const float* b2m, const float* w2v,
+                         const float* b2v, int64_t B, int hidden, int K, int S, int O, int act, float* mean, float* logvar,
+                         float* latent, float* squashed, void* stream);
+MOG_API int mog_air_head_backward(const float* pre1, const float* skip, const float* eps, const float* w1m, const float* b1m,
+                          const float* w1v, const float* b1v, const float* w2m, const float* w2v, const float* logvar,
+                          const float* squashed, const float* g_mean, const float* g_logvar, const float* g_latent,
+                          const float* g_squashed, int64_t B, int hidden, int K, int S, int O, int act, float* dpre1,
+                          float* dskip, float* gw2m, float* gb2m, float* gw2v, float* gb2v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

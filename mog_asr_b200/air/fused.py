@@ -216,3 +216,62 @@ def kl_terms(stacks, temperature, scale_prior_mean, scale_prior_var, vae_prior_m
     ac = stacks["active"].to(torch.bool).contiguous()
     consts = (float(temperature), float(scale_prior_mean), float(scale_prior_var), float(vae_prior_mean), float(vae_prior_var))
     return _KlTerms.apply(ap, ac, consts, *ts)
+
+
+class _FusedHead(torch.autograd.Function):
+    """One (mean, log-variance) head with its sample: first-layer GEMM by the library, everything else in one kernel
+    each way (csrc/mog_air_head.cu).  The parameters are NOT autograd inputs: second-layer gradients are accumulated
+    into their ``.grad`` by the backward kernel, first-layer gradients are formed once per training step from the
+    stashed ``(x, skip, dpre1)`` rows (``_MeanVar.flush_head``) -- the deferred-weight-gradient scheme of the loop."""
+
+    @staticmethod
+    def forward(ctx, x, skip, eps, w1cat, head, act):
+        L = _lib.load()
+        hm, m, hv, v = head.hm, head.m, head.hv, head.v
+        B, K = x.shape
+        h, O = hm.weight.shape[0], m.weight.shape[0]
+        S = 0 if skip is None else skip.shape[1]
+        pre1 = torch.mm(x, w1cat.t())                                   # [B, 2h] = x [W1m | W1v]
+        new = lambda: torch.empty((B, O), dtype=torch.float32, device=x.device)
+        mean, logvar, latent, squashed = new(), new(), new(), (new() if act else None)
+        with torch.cuda.device(x.device):
+            _lib.check(L.mog_air_head_forward(_p(pre1), _p(skip), _p(eps), _p(hm.weight), _p(hm.bias), _p(hv.weight), _p(hv.bias),
+                                              _p(m.weight), _p(m.bias), _p(v.weight), _p(v.bias), B, h, K, S, O, act,
+                                              _p(mean), _p(logvar), _p(latent), _p(squashed), _stream(x)), "mog_air_head_forward")
+        ctx.save_for_backward(x, skip, eps, pre1, logvar, squashed, w1cat)
+        ctx.head, ctx.act, ctx.dims = head, act, (B, h, K, S, O)
+        ctx.set_materialize_grads(False)
+        return mean, logvar, latent, (squashed if act else latent.new_empty(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_mean, g_logvar, g_latent, g_squashed):
+        x, skip, eps, pre1, logvar, squashed, w1cat = ctx.saved_tensors
+        head, act, (B, h, K, S, O) = ctx.head, ctx.act, ctx.dims
+        hm, m, hv, v = head.hm, head.m, head.hv, head.v
+        L = _lib.load()
+        c = lambda g: g.contiguous() if g is not None else None
+        g_mean, g_logvar, g_latent = c(g_mean), c(g_logvar), c(g_latent)
+        g_squashed = c(g_squashed) if act else None
+        for prm in (m.weight, m.bias, v.weight, v.bias):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm)
+        dpre1 = torch.empty_like(pre1)
+        dskip = torch.empty_like(skip) if skip is not None else None
+        with torch.cuda.device(x.device):
+            _lib.check(L.mog_air_head_backward(_p(pre1), _p(skip), _p(eps), _p(hm.weight), _p(hm.bias), _p(hv.weight), _p(hv.bias),
+                                               _p(m.weight), _p(v.weight), _p(logvar), _p(squashed), _p(g_mean), _p(g_logvar),
+                                               _p(g_latent), _p(g_squashed), B, h, K, S, O, act, _p(dpre1), _p(dskip),
+                                               _p(m.weight.grad), _p(m.bias.grad), _p(v.weight.grad), _p(v.bias.grad), _stream(x)),
+                       "mog_air_head_backward")
+        head._head_stash.append((x, skip, dpre1))
+        return torch.mm(dpre1, w1cat), dskip, None, None, None, None
+
+
+def fused_head(head, x, skip, eps, act=None):
+    """``(mean, logvar, latent, squashed)`` of a ``_MeanVar`` head (``head.prepare()`` must have run in this step)."""
+    _need_cuda(x, "x")
+    a = _ACT[act]
+    mean, logvar, latent, squashed = _FusedHead.apply(x.float().contiguous(), None if skip is None else skip.float().contiguous(),
+                                                      eps.float().contiguous(), head._w1cat, head, a)
+    return mean, logvar, latent, (squashed if a else None)

@@ -83,8 +83,9 @@ class CudaOps:
     elementwise math (sampling, theta construction, z_pres) in framework ops, written like the reference -- the
     kernels are still the sampler / composite / regulariser / loss ones; used to check the fused forms."""
 
-    def __init__(self, process_group=None, global_batch=None, fused_pointwise=True):
+    def __init__(self, process_group=None, global_batch=None, fused_pointwise=True, fused_heads=None):
         self.process_group, self.global_batch, self.fused_pointwise = process_group, global_batch, fused_pointwise
+        self.fused_heads = fused_pointwise if fused_heads is None else fused_heads   # csrc/mog_air_head.cu
 
     def transformer(self, U, theta, out_size):
         from ..transformer import transformer
@@ -269,6 +270,8 @@ class _MeanVar(nn.Module):
         super().__init__()
         self.hm, self.m = _dense(in_dim + skip_dim, hidden), _dense(hidden + skip_dim, out_dim)
         self.hv, self.v = _dense(in_dim + skip_dim, hidden), _dense(hidden + skip_dim, out_dim)
+        self.in_dim, self.skip_dim = in_dim, skip_dim
+        self._w1cat, self._head_stash = None, []
 
     def forward(self, x, skip=None):
         if skip is None:
@@ -277,6 +280,46 @@ class _MeanVar(nn.Module):
         mean = self.m(torch.cat([F.relu(self.hm(xs)), skip], -1))
         logvar = self.v(torch.cat([F.relu(self.hv(xs)), skip], -1))
         return mean, logvar
+
+    # ---- fused form (csrc/mog_air_head.cu): one library GEMM + one kernel each way ----------------------------------
+    def fusable(self, ops, x):
+        return (getattr(ops, "fused_heads", False) and self.hm.defer and x.is_cuda and x.dtype == torch.float32
+                and self.hm.weight.shape[0] in (16, 32, 64, 128) and self.m.weight.shape[0] <= 2 and self.skip_dim <= 2)
+
+    def prepare(self):
+        """[W1m | W1v] without the skip columns, rebuilt once per training step (the weights change every step)"""
+        with torch.no_grad():
+            self._w1cat = torch.cat([self.hm.weight[:, :self.in_dim], self.hv.weight[:, :self.in_dim]], 0)   # [2h, K]
+
+    def sample(self, ops, x, eps, act, skip=None):
+        """``(mean, logvar, latent, squashed)``: heads + reparameterised sample (:424-436 / :439-459)"""
+        if self._w1cat is not None and self.fusable(ops, x):
+            from .fused import fused_head
+            return fused_head(self, x, skip, eps, act)
+        mean, logvar = self(x, skip)
+        latent, squashed = ops.gauss_sample(mean, logvar, eps, act)
+        return mean, logvar, latent, squashed
+
+    def flush_head(self):
+        """first-layer weight / bias gradients from the rows stashed by the fused backward (one GEMM per head per step)"""
+        if not self._head_stash:
+            return
+        with torch.no_grad():
+            K, h = self.in_dim, self.hm.weight.shape[0]
+            X = torch.cat([x for x, _, _ in self._head_stash], 0)
+            D = torch.cat([d for _, _, d in self._head_stash], 0)
+            dW = torch.mm(D.t(), X)                                                     # [2h, K]
+            self.hm.weight.grad[:, :K] += dW[:h]
+            self.hv.weight.grad[:, :K] += dW[h:]
+            if self.skip_dim:
+                Sk = torch.cat([s for _, s, _ in self._head_stash], 0)
+                dWs = torch.mm(D.t(), Sk)                                               # [2h, S]
+                self.hm.weight.grad[:, K:] += dWs[:h]
+                self.hv.weight.grad[:, K:] += dWs[h:]
+            db = D.sum(0)
+            self.hm.bias.grad += db[:h]
+            self.hv.bias.grad += db[h:]
+        self._head_stash.clear()
 
 
 class AIRModel(nn.Module):
@@ -306,11 +349,16 @@ class AIRModel(nn.Module):
             if isinstance(m, _StepAffine):
                 m.defer = bool(on)
                 m._stash.clear()
+            if isinstance(m, _MeanVar):
+                m._head_stash.clear()
+                m._w1cat = None
 
     def flush_weight_grads(self):
         for m in self.modules():
             if isinstance(m, _StepAffine):
                 m.flush_grads()
+            if isinstance(m, _MeanVar):
+                m.flush_head()
 
     # ---- pieces -------------------------------------------------------------------------------------------
     def _vae(self, window, eps):
@@ -362,6 +410,10 @@ class AIRModel(nn.Module):
                                                else torch.randn(shape, device=dev, dtype=dt))
         H, L = cfg.rnn_units, cfg.vae_latent_dimensions
         z = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+        if torch.is_grad_enabled():
+            for head in (self.inf_shift, self.inf_scale):
+                if head.fusable(self.ops, images):
+                    head.prepare()
         if cfg.always_max_steps and cfg.batched_tail and cfg.stacked_kl:
             return self._forward_batched_tail(images, noise, global_batch, recon_loss_fn)
         stop_sum = z(B)
@@ -388,10 +440,9 @@ class AIRModel(nn.Module):
             prev = torch.cat([prev_latent, prev_ss], -1)   # input of both cells besides the image / the state
             out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w,
                                              pointwise=lstm_pw)                                             # :413-422
-            sh_mean, sh_lv = self.inf_shift(out)                                                            # :424-431
-            shift_latent, inf_shift = self.ops.gauss_sample(sh_mean, sh_lv, noise("shift", step, (B, 2)), "tanh")    # :433-435
-            sc_mean, sc_lv = self.inf_scale(out, shift_latent)                                              # :439-455
-            scale_latent, inf_scale = self.ops.gauss_sample(sc_mean, sc_lv, noise("scale", step, (B, 1)), "sigmoid")  # :456-458
+            sh_mean, sh_lv, shift_latent, inf_shift = self.inf_shift.sample(self.ops, out, noise("shift", step, (B, 2)), "tanh")   # :424-435
+            sc_mean, sc_lv, scale_latent, inf_scale = self.inf_scale.sample(self.ops, out, noise("scale", step, (B, 1)), "sigmoid",
+                                                                            skip=shift_latent)                                # :439-458
             ss_latent = torch.cat([shift_latent, scale_latent], -1)                                         # :463
             gen_out, gen_state = self.gen_cell(prev, gen_state, pointwise=lstm_pw)                          # :465-470
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
@@ -456,10 +507,9 @@ class AIRModel(nn.Module):
         for step in range(T):
             prev = torch.cat([prev_latent, prev_ss], -1)
             out, inf_state = self.infer_cell(prev, inf_state, static_gates=img_gates, static_width=img_w, pointwise=lstm_pw)
-            sh_mean, sh_lv = self.inf_shift(out)
-            shift_latent, inf_shift = self.ops.gauss_sample(sh_mean, sh_lv, noise("shift", step, (B, 2)), "tanh")
-            sc_mean, sc_lv = self.inf_scale(out, shift_latent)
-            scale_latent, inf_scale = self.ops.gauss_sample(sc_mean, sc_lv, noise("scale", step, (B, 1)), "sigmoid")
+            sh_mean, sh_lv, shift_latent, inf_shift = self.inf_shift.sample(self.ops, out, noise("shift", step, (B, 2)), "tanh")
+            sc_mean, sc_lv, scale_latent, inf_scale = self.inf_scale.sample(self.ops, out, noise("scale", step, (B, 1)), "sigmoid",
+                                                                            skip=shift_latent)
             theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)
             x = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws * ws)   # C = 1: a view, no select
             for l in self.vae_rec:

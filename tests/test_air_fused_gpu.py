@@ -125,3 +125,59 @@ def test_kl_terms(cuda_device, T):
         _check(comps[:, i], p_, rtol=2e-5, atol=1e-4)
     for k in shp:
         _check(st[k].grad, s64[k].grad, rtol=2e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("skip_dim,out_dim,act,B", [(0, 2, "tanh", 300), (2, 1, "sigmoid", 257), (0, 2, "tanh", 3), (2, 1, "sigmoid", 4096)])
+def test_fused_head_matches_framework_ops(cuda_device, skip_dim, out_dim, act, B):
+    """The (mean, log-variance) heads with their sample (:424-460): one library GEMM + one kernel each way against the
+    layer-by-layer framework form -- outputs, input gradients and every parameter gradient (second layer: accumulated by
+    the backward kernel; first layer: from the stashed rows at flush time), over two loop iterations sharing the head."""
+    from mog_asr_b200.air.model import _MeanVar, CudaOps
+    dev = cuda_device
+
+    def close(a, b, rtol, atol):
+        return bool(torch.all((a - b).abs() <= atol + rtol * b.abs()))
+    torch.manual_seed(skip_dim * 10 + out_dim)
+    head = _MeanVar(256, 64, out_dim, skip_dim=skip_dim).to(dev)
+    for prm in head.parameters():                       # zero-initialised biases would hide bias-path errors
+        prm.data.add_(0.05 * torch.randn_like(prm))
+    ops = CudaOps()
+    xs = [torch.randn(B, 256, device=dev, requires_grad=True) for _ in range(2)]
+    sk = [torch.randn(B, skip_dim, device=dev, requires_grad=True) if skip_dim else None for _ in range(2)]
+    eps = [torch.randn(B, out_dim, device=dev) for _ in range(2)]
+    wts = [torch.randn(4, B, out_dim, device=dev) for _ in range(2)]
+
+    def run(fused):
+        for t in xs + [s for s in sk if s is not None]:
+            t.grad = None
+        for prm in head.parameters():
+            prm.grad = torch.zeros_like(prm)
+        for lyr in (head.hm, head.m, head.hv, head.v):
+            lyr.defer = fused
+            lyr._stash.clear()
+        head._head_stash.clear()
+        head._w1cat = None
+        if fused:
+            assert head.fusable(ops, xs[0])
+            head.prepare()
+        outs, loss = [], 0.0
+        for x, s, e, w in zip(xs, sk, eps, wts):
+            o = head.sample(ops, x, e, act, skip=s)
+            outs.append([t.detach().clone() for t in o])
+            loss = loss + sum((wi * oi).sum() for wi, oi in zip(w, o))
+        loss.backward()
+        if fused:
+            head.flush_head()
+            assert not any(lyr._stash for lyr in (head.hm, head.m, head.hv, head.v))
+        grads = [x.grad.clone() for x in xs] + [s.grad.clone() for s in sk if s is not None]
+        return outs, grads, {n: p.grad.clone() for n, p in head.named_parameters()}
+
+    o0, g0, p0 = run(False)
+    o1, g1, p1 = run(True)
+    for a, b in zip(o0, o1):
+        for x, y in zip(a, b):
+            assert close(y, x, 2e-5, 2e-5)
+    for x, y in zip(g0, g1):
+        assert close(y, x, 1e-4, 1e-4 * float(x.abs().max()))
+    for n in p0:
+        assert close(p1[n], p0[n], 2e-4, 2e-4 * float(p0[n].abs().max()) + 1e-6), n
