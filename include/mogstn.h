@@ -226,6 +226,18 @@ MOG_API int mog_air_head_backward(const float* pre1, const float* skip, const fl
                           const float* g_squashed, int64_t B, int hidden, int K, int S, int O, int act, float* dpre1,
                           float* dskip, float* gw2m, float* gb2m, float* gw2v, float* gb2v, void* stream);
 
+/* ---- epilogues of dense layers whose GEMM is the library's -----------------------------------------------------------
+ * bias_act: out[b][n] = act(pre[b][n] + bias[n]), act 0 none / 1 relu / 2 softplus / 3 sigmoid (vae.py:16-19,:34-41;
+ *   :609-623); out may alias pre.  backward: dpre = g * act'(.) from the saved output y (n = B*N elements; dpre may alias g).
+ * bias_gauss: pre [B][2L] = x [Wmean | Wlogvar] -> mean, logvar (biases added) and latent = mean + eps*sqrt(exp(logvar))
+ *   (vae.py:21-31); backward: g_* nullable, dpre [B][2L] fully overwritten. */
+MOG_API int mog_air_bias_act_forward(const float* pre, const float* bias, float* out, int64_t B, int N, int act, void* stream);
+MOG_API int mog_air_bias_act_backward(const float* y, const float* g, float* dpre, int64_t n, int act, void* stream);
+MOG_API int mog_air_bias_gauss_forward(const float* pre, const float* bias_mean, const float* bias_logvar, const float* eps,
+                               float* mean, float* logvar, float* latent, int64_t B, int L, void* stream);
+MOG_API int mog_air_bias_gauss_backward(const float* logvar, const float* eps, const float* g_mean, const float* g_logvar,
+                                const float* g_latent, float* dpre, int64_t B, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -275,3 +275,82 @@ def fused_head(head, x, skip, eps, act=None):
     mean, logvar, latent, squashed = _FusedHead.apply(x.float().contiguous(), None if skip is None else skip.float().contiguous(),
                                                       eps.float().contiguous(), head._w1cat, head, a)
     return mean, logvar, latent, (squashed if a else None)
+
+
+_ACT_DENSE = {None: 0, "none": 0, "relu": 1, "softplus": 2, "sigmoid": 3}
+
+
+class _FusedLinearAct(torch.autograd.Function):
+    """``act(x W^T + b)``: library GEMM + one bias/activation kernel; backward: one activation kernel + library GEMM.
+    The layer's weight / bias gradients go through its deferred stash (``(x, dpre)`` rows, one GEMM per training step)."""
+
+    @staticmethod
+    def forward(ctx, x, layer, act):
+        L = _lib.load()
+        w, bias = layer.weight, layer.bias
+        y = torch.mm(x, w.t())
+        B, N = y.shape
+        with torch.cuda.device(x.device):
+            _lib.check(L.mog_air_bias_act_forward(_p(y), _p(bias), _p(y), B, N, act, _stream(x)), "mog_air_bias_act_forward")
+        ctx.save_for_backward(x, y)
+        ctx.layer, ctx.act = layer, act
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        layer, act = ctx.layer, ctx.act
+        g = g.contiguous()
+        if act:
+            L = _lib.load()
+            dpre = torch.empty_like(g)
+            with torch.cuda.device(x.device):
+                _lib.check(L.mog_air_bias_act_backward(_p(y), _p(g), _p(dpre), g.numel(), act, _stream(x)), "mog_air_bias_act_backward")
+        else:
+            dpre = g
+        layer._stash.append((x, dpre))
+        return torch.mm(dpre, layer.weight), None, None
+
+
+def linear_act(layer, x, act=None):
+    _need_cuda(x, "x")
+    return _FusedLinearAct.apply(x.float().contiguous(), layer, _ACT_DENSE[act])
+
+
+class _FusedLinearGauss(torch.autograd.Function):
+    """mean / log-variance layers sharing their input, plus the sample: one GEMM on ``[Wmean | Wlogvar]`` and one kernel."""
+
+    @staticmethod
+    def forward(ctx, x, eps, pair):
+        L = _lib.load()
+        pre = torch.mm(x, pair.wcat.t())                                  # [B, 2L]
+        B, Ld = x.shape[0], pair.mean_layer.weight.shape[0]
+        new = lambda: torch.empty((B, Ld), dtype=torch.float32, device=x.device)
+        mean, logvar, latent = new(), new(), new()
+        with torch.cuda.device(x.device):
+            _lib.check(L.mog_air_bias_gauss_forward(_p(pre), _p(pair.mean_layer.bias), _p(pair.logvar_layer.bias), _p(eps), _p(mean),
+                                                    _p(logvar), _p(latent), B, Ld, _stream(x)), "mog_air_bias_gauss_forward")
+        ctx.save_for_backward(x, eps, logvar, pair.wcat)
+        ctx.pair = pair
+        ctx.set_materialize_grads(False)
+        return mean, logvar, latent
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_mean, g_logvar, g_latent):
+        x, eps, logvar, wcat = ctx.saved_tensors
+        L = _lib.load()
+        c = lambda g: g.contiguous() if g is not None else None
+        B, Ld = logvar.shape
+        dpre = torch.empty((B, 2 * Ld), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.mog_air_bias_gauss_backward(_p(logvar), _p(eps), _p(c(g_mean)), _p(c(g_logvar)), _p(c(g_latent)), _p(dpre), B, Ld,
+                                                     _stream(x)), "mog_air_bias_gauss_backward")
+        ctx.pair.stash.append((x, dpre))
+        return torch.mm(dpre, wcat), None, None
+
+
+def linear_gauss(pair, x, eps):
+    _need_cuda(x, "x")
+    return _FusedLinearGauss.apply(x.float().contiguous(), eps.float().contiguous(), pair)

@@ -208,9 +208,15 @@ class StepLinear(nn.Module, _StepAffine):
         self.bias = nn.Parameter(torch.zeros(o))
         nn.init.xavier_uniform_(self.weight)
         self._init_defer()
+        self.fuse = False        # set by AIRModel when its ops object offers the fused epilogues
 
-    def forward(self, x):
-        return self._affine(x, self.weight.t(), self.bias)
+    def forward(self, x, act=None):
+        """``act(x W^T + b)`` with ``act`` in None / 'relu' / 'softplus' / 'sigmoid'"""
+        if self.fuse and self.defer and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled():
+            from .fused import linear_act                      # library GEMM + one bias/activation kernel each way
+            return linear_act(self, x, act)
+        y = self._affine(x, self.weight.t(), self.bias)
+        return y if act is None else {"relu": F.relu, "softplus": F.softplus, "sigmoid": torch.sigmoid}[act](y)
 
     def flush_grads(self):
         self.flush(self.weight.grad.t(), self.bias.grad)
@@ -275,10 +281,10 @@ class _MeanVar(nn.Module):
 
     def forward(self, x, skip=None):
         if skip is None:
-            return self.m(F.relu(self.hm(x))), self.v(F.relu(self.hv(x)))
+            return self.m(self.hm(x, "relu")), self.v(self.hv(x, "relu"))
         xs = torch.cat([x, skip], -1)                       # shared by the mean and the log-variance branch
-        mean = self.m(torch.cat([F.relu(self.hm(xs)), skip], -1))
-        logvar = self.v(torch.cat([F.relu(self.hv(xs)), skip], -1))
+        mean = self.m(torch.cat([self.hm(xs, "relu"), skip], -1))
+        logvar = self.v(torch.cat([self.hv(xs, "relu"), skip], -1))
         return mean, logvar
 
     # ---- fused form (csrc/mog_air_head.cu): one library GEMM + one kernel each way ----------------------------------
@@ -322,6 +328,41 @@ class _MeanVar(nn.Module):
         self._head_stash.clear()
 
 
+class _GaussPair:
+    """mean / log-variance layers that share their input and feed one sample (vae.py:21-31): evaluated as one GEMM on the
+    concatenated weights plus one kernel; their gradients come from the stashed ``(x, dpre)`` rows at flush time."""
+
+    def __init__(self, mean_layer, logvar_layer):
+        self.mean_layer, self.logvar_layer, self.wcat, self.stash = mean_layer, logvar_layer, None, []
+
+    def usable(self, x):
+        return (self.wcat is not None and self.mean_layer.fuse and self.mean_layer.defer and x.is_cuda and x.dtype == torch.float32
+                and torch.is_grad_enabled())
+
+    def prepare(self):
+        with torch.no_grad():
+            self.wcat = torch.cat([self.mean_layer.weight, self.logvar_layer.weight], 0)      # [2L, in]
+
+    def reset(self):
+        self.wcat = None
+        self.stash.clear()
+
+    def flush(self):
+        if not self.stash:
+            return
+        with torch.no_grad():
+            Ld = self.mean_layer.weight.shape[0]
+            X = torch.cat([x for x, _ in self.stash], 0)
+            D = torch.cat([d for _, d in self.stash], 0)
+            dW = torch.mm(D.t(), X)
+            self.mean_layer.weight.grad += dW[:Ld]
+            self.logvar_layer.weight.grad += dW[Ld:]
+            db = D.sum(0)
+            self.mean_layer.bias.grad += db[:Ld]
+            self.logvar_layer.bias.grad += db[Ld:]
+        self.stash.clear()
+
+
 class AIRModel(nn.Module):
     """Training graph of the reference ``AIRModel`` (``train=True``)."""
 
@@ -342,6 +383,10 @@ class AIRModel(nn.Module):
         if cfg.fix_steps is None:
             self.z_prior_h, self.z_prior = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)  # :609-615
         self.z_post_h, self.z_post = _dense(H, cfg.z_pres_hidden_units), _dense(cfg.z_pres_hidden_units, 1)        # :620-623
+        for m in self.modules():
+            if isinstance(m, StepLinear):
+                m.fuse = bool(getattr(self.ops, "fused_heads", False))
+        self._vae_pair = _GaussPair(self.vae_rec_mean, self.vae_rec_logvar)
 
     # ---- deferred weight gradients (see _DeferredAffine) ------------------------------------------------------
     def set_deferred_weight_grads(self, on: bool):
@@ -352,6 +397,7 @@ class AIRModel(nn.Module):
             if isinstance(m, _MeanVar):
                 m._head_stash.clear()
                 m._w1cat = None
+        self._vae_pair.reset()
 
     def flush_weight_grads(self):
         for m in self.modules():
@@ -359,19 +405,32 @@ class AIRModel(nn.Module):
                 m.flush_grads()
             if isinstance(m, _MeanVar):
                 m.flush_head()
+        self._vae_pair.flush()
 
     # ---- pieces -------------------------------------------------------------------------------------------
-    def _vae(self, window, eps):
-        """air/vae.py:5-48 (softplus hidden layers, sigmoid output; likelihood_std = 0 drops the second noise)."""
+    def _encode(self, window, eps):
+        """recognition half of air/vae.py:5-31: softplus layers, mean / log-variance, sample"""
         x = window
         for l in self.vae_rec:
-            x = F.softplus(l(x))
+            x = l(x, "softplus")
+        if self._vae_pair.usable(x):
+            from .fused import linear_gauss
+            return linear_gauss(self._vae_pair, x, eps)
         mean, logvar = self.vae_rec_mean(x), self.vae_rec_logvar(x)
         latent, _ = self.ops.gauss_sample(mean, logvar, eps)                 # vae.py:28-31
+        return mean, logvar, latent
+
+    def _decode(self, latent):
+        """generative half (vae.py:34-41); likelihood_std = 0 drops the second noise"""
         x = latent
         for l in self.vae_gen:
-            x = F.softplus(l(x))
-        return torch.sigmoid(self.vae_gen_mean(x)), mean, logvar, latent
+            x = l(x, "softplus")
+        return self.vae_gen_mean(x, "sigmoid")
+
+    def _vae(self, window, eps):
+        """air/vae.py:5-48 (softplus hidden layers, sigmoid output)"""
+        mean, logvar, latent = self._encode(window, eps)
+        return self._decode(latent), mean, logvar, latent
 
     @staticmethod
     def _concrete_kl(y, prior_lo, post_lo, temp, eps=10e-10):
@@ -414,6 +473,8 @@ class AIRModel(nn.Module):
             for head in (self.inf_shift, self.inf_scale):
                 if head.fusable(self.ops, images):
                     head.prepare()
+            if self.vae_rec_mean.fuse and self.vae_rec_mean.defer and images.is_cuda and images.dtype == torch.float32:
+                self._vae_pair.prepare()
         if cfg.always_max_steps and cfg.batched_tail and cfg.stacked_kl:
             return self._forward_batched_tail(images, noise, global_batch, recon_loss_fn)
         stop_sum = z(B)
@@ -454,8 +515,8 @@ class AIRModel(nn.Module):
             if cfg.fix_steps is not None:                                                                   # :604-608
                 prior_lo = torch.full((B,), 100.0 if step < cfg.fix_steps else -100.0, device=dev, dtype=dt)
             else:
-                prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev_out))).reshape(B)                     # :609-615
-            post_lo = self.z_post(F.relu(self.z_post_h(out))).reshape(B)                                     # :620-623
+                prior_lo = self.z_prior(self.z_prior_h(gen_prev_out, "relu")).reshape(B)                     # :609-615
+            post_lo = self.z_post(self.z_post_h(out, "relu")).reshape(B)                                     # :620-623
             y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
                                                                           temp, thr)     # concrete.py:20-27, :631, :698-712
             act_list.append(active)
@@ -512,10 +573,7 @@ class AIRModel(nn.Module):
                                                                             skip=shift_latent)
             theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)
             x = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws * ws)   # C = 1: a view, no select
-            for l in self.vae_rec:
-                x = F.softplus(l(x))
-            v_mean, v_lv = self.vae_rec_mean(x), self.vae_rec_logvar(x)
-            v_latent, _ = self.ops.gauss_sample(v_mean, v_lv, noise("vae", step, (B, L)))
+            v_mean, v_lv, v_latent = self._encode(x, noise("vae", step, (B, L)))
             for k, v in (("out", out), ("prev", prev), ("latent", v_latent), ("theta_w", theta_w), ("sc_mean", sc_mean),
                          ("sc_lv", sc_lv), ("sh_mean", sh_mean), ("sh_lv", sh_lv), ("v_mean", v_mean), ("v_lv", v_lv),
                          ("shift", inf_shift), ("scale", inf_scale)):
@@ -535,14 +593,11 @@ class AIRModel(nn.Module):
             prior_lo[:cfg.fix_steps] = 100.0
         else:
             gen_prev = torch.cat([z(B, H)] + gen_outs[:-1], 0)
-            prior_lo = self.z_prior(F.relu(self.z_prior_h(gen_prev))).reshape(T, B)                    # :609-615
-        post_lo = self.z_post(F.relu(self.z_post_h(torch.cat(per["out"], 0)))).reshape(T, B)            # :620-623
+            prior_lo = self.z_prior(self.z_prior_h(gen_prev, "relu")).reshape(T, B)                    # :609-615
+        post_lo = self.z_post(self.z_post_h(torch.cat(per["out"], 0), "relu")).reshape(T, B)            # :620-623
 
         # ---- VAE decoder for all steps (vae.py:34-41) ----------------------------------------------------------
-        x = torch.cat(per["latent"], 0)
-        for l in self.vae_gen:
-            x = F.softplus(l(x))
-        recon = torch.sigmoid(self.vae_gen_mean(x)).reshape(T, B, ws, ws).unbind(0)
+        recon = self._decode(torch.cat(per["latent"], 0)).reshape(T, B, ws, ws).unbind(0)
 
         # ---- Concrete / stopping-sum scan and the canvas writes, in step order -----------------------------------
         stop_sum, canvas = z(B), z(B, cs, cs)

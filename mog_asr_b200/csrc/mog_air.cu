@@ -225,6 +225,57 @@ __global__ void __launch_bounds__(128) air_kl_kernel(const KlArgs a) {
     }
 }
 
+
+// ---- bias + activation epilogue of a dense layer (the GEMM itself is the library's) -------------------------------------
+// act: 0 none, 1 relu, 2 softplus (beta 1, linear above 20 like the framework op), 3 sigmoid.  out may alias pre.
+__global__ void air_bias_act_fwd(const float* __restrict__ pre, const float* __restrict__ bias, float* __restrict__ out, long long n,
+                                 int N, int act) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const float v = pre[k] + bias[(int)(k % N)];
+        float y = v;
+        if (act == 1) y = fmaxf(v, 0.0f);
+        else if (act == 2) y = v > 20.0f ? v : log1pf(expf(v));
+        else if (act == 3) y = 1.0f / (1.0f + expf(-v));
+        out[k] = y;
+    }
+}
+// dpre = g * act'(.) expressed through the saved OUTPUT y; dpre may alias g
+__global__ void air_bias_act_bwd(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ dpre, long long n, int act) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const float o = y[k];
+        float d = g[k];
+        if (act == 1) d = o > 0.0f ? d : 0.0f;
+        else if (act == 2) d = o > 20.0f ? d : d * (1.0f - expf(-o));     // sigmoid(v) = 1 - exp(-softplus(v))
+        else if (act == 3) d = d * o * (1.0f - o);
+        dpre[k] = d;
+    }
+}
+// pre [B][2L] = x [Wmean | Wlogvar]: add the biases, split, draw the sample (vae.py:21-31)
+__global__ void air_bias_gauss_fwd(const float* __restrict__ pre, const float* __restrict__ bm, const float* __restrict__ bv,
+                                   const float* __restrict__ eps, float* __restrict__ mean, float* __restrict__ logvar,
+                                   float* __restrict__ latent, long long B, int Ld) {
+    const long long n = B * Ld;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long b = k / Ld;
+        const int l = (int)(k - b * Ld);
+        const float m = pre[b * 2 * Ld + l] + bm[l], lv = pre[b * 2 * Ld + Ld + l] + bv[l];
+        mean[k] = m; logvar[k] = lv;
+        latent[k] = m + eps[k] * sqrtf(expf(lv));
+    }
+}
+__global__ void air_bias_gauss_bwd(const float* __restrict__ logvar, const float* __restrict__ eps, const float* __restrict__ g_mean,
+                                   const float* __restrict__ g_logvar, const float* __restrict__ g_latent, float* __restrict__ dpre,
+                                   long long B, int Ld) {
+    const long long n = B * Ld;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const long long b = k / Ld;
+        const int l = (int)(k - b * Ld);
+        const float dl = g_latent ? g_latent[k] : 0.0f;
+        dpre[b * 2 * Ld + l] = (g_mean ? g_mean[k] : 0.0f) + dl;
+        dpre[b * 2 * Ld + Ld + l] = (g_logvar ? g_logvar[k] : 0.0f) + dl * eps[k] * 0.5f * sqrtf(expf(logvar[k]));
+    }
+}
+
 }  // namespace mog
 
 using namespace mog;
@@ -368,5 +419,45 @@ extern "C" int mog_air_zpres_backward(const float* z_pres, const float* g_y, con
     MOG_REQUIRE(z_pres && d_log_odds, MOG_ERR_NULL, "zpres backward: NULL pointer");
     air_zpres_bwd<<<air_blocks(B), kAirThreads, 0, (cudaStream_t)stream>>>(z_pres, g_y, g_z, temperature, d_log_odds, B);
     MOG_CUDA_LAUNCH_CHECK("air_zpres_bwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_bias_act_forward(const float* pre, const float* bias, float* out, int64_t B, int N, int act, void* stream) {
+    MOG_REQUIRE(B >= 0 && N > 0 && act >= 0 && act <= 3, MOG_ERR_DIM, "bias_act: B=%lld N=%d act=%d", (long long)B, N, act);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(pre && bias && out, MOG_ERR_NULL, "bias_act forward: NULL pointer");
+    air_bias_act_fwd<<<air_blocks(B * (long long)N), kAirThreads, 0, (cudaStream_t)stream>>>(pre, bias, out, B * (long long)N, N, act);
+    MOG_CUDA_LAUNCH_CHECK("air_bias_act_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_bias_act_backward(const float* y, const float* g, float* dpre, int64_t n, int act, void* stream) {
+    MOG_REQUIRE(n >= 0 && act >= 0 && act <= 3, MOG_ERR_DIM, "bias_act: n=%lld act=%d", (long long)n, act);
+    if (n == 0) return MOG_OK;
+    MOG_REQUIRE(y && g && dpre, MOG_ERR_NULL, "bias_act backward: NULL pointer");
+    air_bias_act_bwd<<<air_blocks(n), kAirThreads, 0, (cudaStream_t)stream>>>(y, g, dpre, n, act);
+    MOG_CUDA_LAUNCH_CHECK("air_bias_act_bwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_bias_gauss_forward(const float* pre, const float* bias_mean, const float* bias_logvar, const float* eps,
+                                          float* mean, float* logvar, float* latent, int64_t B, int L, void* stream) {
+    MOG_REQUIRE(B >= 0 && L > 0, MOG_ERR_DIM, "bias_gauss: B=%lld L=%d", (long long)B, L);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(pre && bias_mean && bias_logvar && eps && mean && logvar && latent, MOG_ERR_NULL, "bias_gauss forward: NULL pointer");
+    air_bias_gauss_fwd<<<air_blocks(B * (long long)L), kAirThreads, 0, (cudaStream_t)stream>>>(pre, bias_mean, bias_logvar, eps, mean,
+                                                                                           logvar, latent, B, L);
+    MOG_CUDA_LAUNCH_CHECK("air_bias_gauss_fwd");
+    return MOG_OK;
+}
+
+extern "C" int mog_air_bias_gauss_backward(const float* logvar, const float* eps, const float* g_mean, const float* g_logvar,
+                                           const float* g_latent, float* dpre, int64_t B, int L, void* stream) {
+    MOG_REQUIRE(B >= 0 && L > 0, MOG_ERR_DIM, "bias_gauss: B=%lld L=%d", (long long)B, L);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(logvar && eps && dpre, MOG_ERR_NULL, "bias_gauss backward: NULL pointer");
+    air_bias_gauss_bwd<<<air_blocks(B * (long long)L), kAirThreads, 0, (cudaStream_t)stream>>>(logvar, eps, g_mean, g_logvar, g_latent,
+                                                                                           dpre, B, L);
+    MOG_CUDA_LAUNCH_CHECK("air_bias_gauss_bwd");
     return MOG_OK;
 }

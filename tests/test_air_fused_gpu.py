@@ -5,6 +5,7 @@ import pytest
 import torch
 
 from mog_asr_b200.air import fused
+from mog_asr_b200.air import fused as fused_mod
 from oracle.air_ops import OracleOps
 
 pytestmark = pytest.mark.gpu
@@ -181,3 +182,71 @@ def test_fused_head_matches_framework_ops(cuda_device, skip_dim, out_dim, act, B
         assert close(y, x, 1e-4, 1e-4 * float(x.abs().max()))
     for n in p0:
         assert close(p1[n], p0[n], 2e-4, 2e-4 * float(p0[n].abs().max()) + 1e-6), n
+
+
+@pytest.mark.parametrize("act", [None, "relu", "softplus", "sigmoid"])
+def test_fused_dense_epilogue_matches_framework_ops(cuda_device, act):
+    """act(x W^T + b) as library GEMM + one kernel each way, weight / bias gradients through the deferred stash."""
+    from mog_asr_b200.air.model import StepLinear
+    torch.manual_seed(3)
+    lyr = StepLinear(96, 40).to(cuda_device)
+    lyr.bias.data.normal_(0, 0.3)
+    xs = [(3.0 * torch.randn(70, 96, device=cuda_device)).requires_grad_(True) for _ in range(2)]
+    ws = [torch.randn(70, 40, device=cuda_device) for _ in range(2)]
+    res = []
+    for fused in (False, True):
+        lyr.fuse, lyr.defer = fused, fused
+        lyr._stash.clear()
+        lyr.weight.grad, lyr.bias.grad = torch.zeros_like(lyr.weight), torch.zeros_like(lyr.bias)
+        for x in xs:
+            x.grad = None
+        ys = [lyr(x, act) for x in xs]
+        sum((y * w).sum() for y, w in zip(ys, ws)).backward()
+        if fused:
+            assert len(lyr._stash) == 2
+            lyr.flush_grads()
+        res.append(([y.detach().clone() for y in ys], [x.grad.clone() for x in xs], lyr.weight.grad.clone(), lyr.bias.grad.clone()))
+    (y0, g0, w0, b0), (y1, g1, w1, b1) = res
+    for a, b in zip(y0 + g0 + [w0, b0], y1 + g1 + [w1, b1]):
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max()))
+
+
+def test_fused_mean_logvar_pair_matches_framework_ops(cuda_device):
+    """vae.py:21-31: mean and log-variance layers on one GEMM, biases + sample in one kernel, gradients at flush time."""
+    from mog_asr_b200.air.model import StepLinear, _GaussPair, CudaOps
+    torch.manual_seed(4)
+    lm, lv = StepLinear(256, 50).to(cuda_device), StepLinear(256, 50).to(cuda_device)
+    for l in (lm, lv):
+        l.bias.data.normal_(0, 0.2)
+    pair, ops = _GaussPair(lm, lv), CudaOps()
+    xs = [torch.randn(130, 256, device=cuda_device, requires_grad=True) for _ in range(2)]
+    eps = [torch.randn(130, 50, device=cuda_device) for _ in range(2)]
+    ws = [torch.randn(3, 130, 50, device=cuda_device) for _ in range(2)]
+    res = []
+    for fused in (False, True):
+        for l in (lm, lv):
+            l.fuse, l.defer = fused, fused
+            l._stash.clear()
+            l.weight.grad, l.bias.grad = torch.zeros_like(l.weight), torch.zeros_like(l.bias)
+        pair.reset()
+        for x in xs:
+            x.grad = None
+        outs, loss = [], 0.0
+        for x, e, w in zip(xs, eps, ws):
+            if fused:
+                pair.prepare()
+                assert pair.usable(x)
+                o = fused_mod.linear_gauss(pair, x, e)
+            else:
+                m, v = lm(x), lv(x)
+                o = (m, v, ops.gauss_sample(m, v, e)[0])
+            outs.append([t.detach().clone() for t in o])
+            loss = loss + sum((wi * oi).sum() for wi, oi in zip(w, o))
+        loss.backward()
+        if fused:
+            pair.flush()
+        res.append((outs, [x.grad.clone() for x in xs], [p.grad.clone() for l in (lm, lv) for p in (l.weight, l.bias)]))
+    (o0, g0, p0), (o1, g1, p1) = res
+    flat = lambda o: [t for step in o for t in step]
+    for a, b in zip(flat(o0) + g0 + p0, flat(o1) + g1 + p1):
+        assert float((a - b).abs().max()) <= 3e-5 * max(1.0, float(a.abs().max()))
