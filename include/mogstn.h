@@ -154,11 +154,14 @@ MOG_API int mog_air_zpres_backward(const float* z_pres, const float* g_y, const 
                            float* d_log_odds, int64_t B, void* stream);
 
 /* LSTM cell pointwise part (tf.nn.rnn_cell.LSTMCell, air_number_bbox_location.py:865-872): gates [B][4H] in the order
- * i, j, f, o; c' = sigmoid(f + 1)*c + sigmoid(i)*tanh(j); h' = sigmoid(o)*tanh(c').  backward: g_h / g_c nullable. */
-MOG_API int mog_air_lstm_pointwise_forward(const float* gates, const float* c_prev, float* c_new, float* h_new, int64_t B,
-                                   int H, void* stream);
-MOG_API int mog_air_lstm_pointwise_backward(const float* gates, const float* c_prev, const float* c_new, const float* g_h,
-                                    const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H, void* stream);
+ * i, j, f, o; c' = sigmoid(f + 1)*c + sigmoid(i)*tanh(j); h' = sigmoid(o)*tanh(c').  gates2 (nullable) is added to gates
+ * first (the step-invariant part of the cell input, computed once per training step); d_gates is the gradient w.r.t. the
+ * sum, i.e. w.r.t. both.  backward: g_h / g_c nullable. */
+MOG_API int mog_air_lstm_pointwise_forward(const float* gates, const float* gates2, const float* c_prev, float* c_new, float* h_new,
+                                   int64_t B, int H, void* stream);
+MOG_API int mog_air_lstm_pointwise_backward(const float* gates, const float* gates2, const float* c_prev, const float* c_new,
+                                    const float* g_h, const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H,
+                                    void* stream);
 
 /* The four KL terms of the ELBO for all executed steps at once (air_number_bbox_location.py:690-787, masked and summed
  * as at :930-935).  Inputs are [T][B][..] stacks: y_pre / prior_lo / post_lo [T][B] (Concrete KL, air/concrete.py:30-64,

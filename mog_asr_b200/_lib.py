@@ -47,8 +47,8 @@ SIGNATURES = {
     "mog_air_thetas_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mog_air_zpres_forward": [_vp, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "mog_air_zpres_backward": [_vp, _vp, _vp, _f32, _vp, _i64, _vp],
-    "mog_air_lstm_pointwise_forward": [_vp, _vp, _vp, _vp, _i64, _int, _vp],
-    "mog_air_lstm_pointwise_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_lstm_pointwise_forward": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
+    "mog_air_lstm_pointwise_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _vp],
     "mog_air_kl_forward": [_vp] * 13 + [_i64, _int, _int, _f32, _f32, _f32, _f32, _f32, _vp, _vp, _vp],
     "mog_air_kl_backward": [_vp] * 13 + [_i64, _int, _int, _f32, _f32, _f32, _f32, _f32] + [_vp] * 12 + [_vp],
     "mog_detection_eval": [_vp] * 6 + [_i64, _int, _int, _f64] + [_vp] * 5 + [_vp],

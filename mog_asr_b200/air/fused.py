@@ -125,36 +125,37 @@ def zpres(log_odds, u, stop_sum, temperature, threshold):
 
 class _LstmPointwise(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gates, c_prev):
+    def forward(ctx, gates, c_prev, gates2):
         L = _lib.load()
         B, H = c_prev.shape
         c_new, h_new = torch.empty_like(c_prev), torch.empty_like(c_prev)
         with torch.cuda.device(gates.device):
-            _lib.check(L.mog_air_lstm_pointwise_forward(_p(gates), _p(c_prev), _p(c_new), _p(h_new), B, H, _stream(gates)),
+            _lib.check(L.mog_air_lstm_pointwise_forward(_p(gates), _p(gates2), _p(c_prev), _p(c_new), _p(h_new), B, H, _stream(gates)),
                        "mog_air_lstm_pointwise_forward")
-        ctx.save_for_backward(gates, c_prev, c_new)
+        ctx.save_for_backward(gates, c_prev, c_new, gates2)
         return c_new, h_new
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_c, g_h):
-        gates, c_prev, c_new = ctx.saved_tensors
+        gates, c_prev, c_new, gates2 = ctx.saved_tensors
         L = _lib.load()
         B, H = c_prev.shape
         g_c = g_c.contiguous() if g_c is not None else None
         g_h = g_h.contiguous() if g_h is not None else None
         d_gates, d_c_prev = torch.empty_like(gates), torch.empty_like(c_prev)
         with torch.cuda.device(gates.device):
-            _lib.check(L.mog_air_lstm_pointwise_backward(_p(gates), _p(c_prev), _p(c_new), _p(g_h), _p(g_c), _p(d_gates),
+            _lib.check(L.mog_air_lstm_pointwise_backward(_p(gates), _p(gates2), _p(c_prev), _p(c_new), _p(g_h), _p(g_c), _p(d_gates),
                                                          _p(d_c_prev), B, H, _stream(gates)), "mog_air_lstm_pointwise_backward")
-        return d_gates, d_c_prev
+        return d_gates, d_c_prev, (d_gates if gates2 is not None else None)
 
 
-def lstm_pointwise(gates, c_prev):
-    """``gates [B,4H]`` (i, j, f, o) and ``c_prev [B,H]`` -> ``(c_new, h_new)`` with ``forget_bias = 1``."""
+def lstm_pointwise(gates, c_prev, gates2=None):
+    """``gates (+ gates2) [B,4H]`` (i, j, f, o) and ``c_prev [B,H]`` -> ``(c_new, h_new)`` with ``forget_bias = 1``."""
     _need_cuda(gates, "gates")
     _need_cuda(c_prev, "c_prev")
-    return _LstmPointwise.apply(gates.float().contiguous(), c_prev.float().contiguous())
+    return _LstmPointwise.apply(gates.float().contiguous(), c_prev.float().contiguous(),
+                                None if gates2 is None else gates2.float().contiguous())
 
 
 _KL_KEYS = ("y_pre", "prior_lo", "post_lo", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "g_sh_mean", "g_sh_lv", "v_mean", "v_lv")

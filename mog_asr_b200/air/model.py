@@ -162,8 +162,8 @@ class _DeferredAffine(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, base, stash, base_is_bias):
         ctx.save_for_backward(x, w)
-        ctx.stash, ctx.base_is_bias = stash, base_is_bias
-        return torch.addmm(base, x, w)
+        ctx.stash, ctx.base_is_bias = stash, base_is_bias or base is None
+        return torch.mm(x, w) if base is None else torch.addmm(base, x, w)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -246,6 +246,11 @@ class LSTMCellTF(nn.Module, _StepAffine):
         c, h = state
         self._static_width = static_width if static_gates is not None else 0
         xh = h if x.shape[1] == 0 else torch.cat([x, h], 1)
+        if static_gates is not None and pointwise is not None and self.defer and torch.is_grad_enabled():
+            # the static part (which carries the bias) is added inside the gate kernel: plain GEMM, no accumulate-into-a-copy
+            dyn = _DeferredAffine.apply(xh, self.kernel[static_width:], None, self._stash, True)
+            c2, h2 = pointwise(dyn, c, static_gates)
+            return h2, (c2, h2)
         if static_gates is None:
             gates = self._affine(xh, self.kernel, self.bias)
         else:

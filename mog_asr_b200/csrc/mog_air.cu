@@ -95,15 +95,22 @@ __global__ void air_zpres_bwd(const float* __restrict__ z_pres, const float* __r
 
 // LSTM cell pointwise part (tf.nn.rnn_cell.LSTMCell, :865-872): gates [B][4H] in the order i, j, f, o,
 // c' = sigmoid(f + 1)*c + sigmoid(i)*tanh(j),  h' = sigmoid(o)*tanh(c')   (forget_bias = 1)
-__global__ void air_lstm_fwd(const float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_new,
-                             float* __restrict__ h_new, long long B, int H) {
+// gates2 (nullable): a second addend of the gate pre-activations (the part of the LSTM input that is the same at every
+// step, computed once), so that the per-step GEMM does not need an accumulate-into-a-copy
+__global__ void air_lstm_fwd(const float* __restrict__ gates, const float* __restrict__ gates2, const float* __restrict__ c_prev,
+                             float* __restrict__ c_new, float* __restrict__ h_new, long long B, int H) {
     const long long n = B * (long long)H;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const long long b = k / H;
         const int u = (int)(k - b * H);
         const float* gr = gates + b * 4 * H;
-        const float i = 1.0f / (1.0f + expf(-gr[u])), j = tanhf(gr[H + u]);
-        const float f = 1.0f / (1.0f + expf(-(gr[2 * H + u] + 1.0f))), o = 1.0f / (1.0f + expf(-gr[3 * H + u]));
+        float gi = gr[u], gj = gr[H + u], gf = gr[2 * H + u], go = gr[3 * H + u];
+        if (gates2) {
+            const float* g2 = gates2 + b * 4 * H;
+            gi += g2[u]; gj += g2[H + u]; gf += g2[2 * H + u]; go += g2[3 * H + u];
+        }
+        const float i = 1.0f / (1.0f + expf(-gi)), j = tanhf(gj);
+        const float f = 1.0f / (1.0f + expf(-(gf + 1.0f))), o = 1.0f / (1.0f + expf(-go));
         const float c = f * c_prev[k] + i * j;
         c_new[k] = c;
         h_new[k] = o * tanhf(c);
@@ -111,17 +118,22 @@ __global__ void air_lstm_fwd(const float* __restrict__ gates, const float* __res
 }
 
 // g_h / g_c nullable (gradients w.r.t. h' and c'); d_gates [B][4H], d_c_prev [B][H] fully overwritten
-__global__ void air_lstm_bwd(const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_new,
-                             const float* __restrict__ g_h, const float* __restrict__ g_c, float* __restrict__ d_gates,
-                             float* __restrict__ d_c_prev, long long B, int H) {
+__global__ void air_lstm_bwd(const float* __restrict__ gates, const float* __restrict__ gates2, const float* __restrict__ c_prev,
+                             const float* __restrict__ c_new, const float* __restrict__ g_h, const float* __restrict__ g_c,
+                             float* __restrict__ d_gates, float* __restrict__ d_c_prev, long long B, int H) {
     const long long n = B * (long long)H;
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const long long b = k / H;
         const int u = (int)(k - b * H);
         const float* gr = gates + b * 4 * H;
         float* dg = d_gates + b * 4 * H;
-        const float i = 1.0f / (1.0f + expf(-gr[u])), j = tanhf(gr[H + u]);
-        const float f = 1.0f / (1.0f + expf(-(gr[2 * H + u] + 1.0f))), o = 1.0f / (1.0f + expf(-gr[3 * H + u]));
+        float gi = gr[u], gj = gr[H + u], gf = gr[2 * H + u], go = gr[3 * H + u];
+        if (gates2) {
+            const float* g2 = gates2 + b * 4 * H;
+            gi += g2[u]; gj += g2[H + u]; gf += g2[2 * H + u]; go += g2[3 * H + u];
+        }
+        const float i = 1.0f / (1.0f + expf(-gi)), j = tanhf(gj);
+        const float f = 1.0f / (1.0f + expf(-(gf + 1.0f))), o = 1.0f / (1.0f + expf(-go));
         const float tc = tanhf(c_new[k]);
         const float dh = g_h ? g_h[k] : 0.0f;
         const float dc = (g_c ? g_c[k] : 0.0f) + dh * o * (1.0f - tc * tc);
@@ -333,23 +345,23 @@ extern "C" int mog_air_kl_backward(const float* y_pre, const float* prior_lo, co
 }
 
 
-extern "C" int mog_air_lstm_pointwise_forward(const float* gates, const float* c_prev, float* c_new, float* h_new, int64_t B,
+extern "C" int mog_air_lstm_pointwise_forward(const float* gates, const float* gates2, const float* c_prev, float* c_new, float* h_new, int64_t B,
                                               int H, void* stream) {
     MOG_REQUIRE(B >= 0 && H > 0, MOG_ERR_DIM, "lstm pointwise: B=%lld H=%d", (long long)B, H);
     if (B == 0) return MOG_OK;
     MOG_REQUIRE(gates && c_prev && c_new && h_new, MOG_ERR_NULL, "lstm pointwise forward: NULL pointer");
-    air_lstm_fwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, h_new, B, H);
+    air_lstm_fwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, gates2, c_prev, c_new, h_new, B, H);
     MOG_CUDA_LAUNCH_CHECK("air_lstm_fwd");
     return MOG_OK;
 }
 
-extern "C" int mog_air_lstm_pointwise_backward(const float* gates, const float* c_prev, const float* c_new, const float* g_h,
+extern "C" int mog_air_lstm_pointwise_backward(const float* gates, const float* gates2, const float* c_prev, const float* c_new, const float* g_h,
                                                const float* g_c, float* d_gates, float* d_c_prev, int64_t B, int H,
                                                void* stream) {
     MOG_REQUIRE(B >= 0 && H > 0, MOG_ERR_DIM, "lstm pointwise: B=%lld H=%d", (long long)B, H);
     if (B == 0) return MOG_OK;
     MOG_REQUIRE(gates && c_prev && c_new && d_gates && d_c_prev, MOG_ERR_NULL, "lstm pointwise backward: NULL pointer");
-    air_lstm_bwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, c_prev, c_new, g_h, g_c, d_gates,
+    air_lstm_bwd<<<air_blocks(B * (long long)H), kAirThreads, 0, (cudaStream_t)stream>>>(gates, gates2, c_prev, c_new, g_h, g_c, d_gates,
                                                                                        d_c_prev, B, H);
     MOG_CUDA_LAUNCH_CHECK("air_lstm_bwd");
     return MOG_OK;

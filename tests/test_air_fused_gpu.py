@@ -78,15 +78,19 @@ def test_zpres(cuda_device, temp):
     _check(lo.grad, lo64.grad, rtol=1e-5, atol=1e-6)
 
 
-def test_lstm_pointwise(cuda_device):
+@pytest.mark.parametrize("split", [False, True])
+def test_lstm_pointwise(cuda_device, split):
+    """``split``: the gate pre-activations arrive as two addends (per-step GEMM + the step-invariant part)"""
     g = torch.Generator(device=cuda_device).manual_seed(4)
     B, Hh = 37, 256
     gates = torch.randn((B, 4 * Hh), device=cuda_device, generator=g).requires_grad_(True)
+    gates2 = torch.randn((B, 4 * Hh), device=cuda_device, generator=g).requires_grad_(True) if split else None
     c = torch.randn((B, Hh), device=cuda_device, generator=g).requires_grad_(True)
     gc, gh = torch.randn((B, Hh), device=cuda_device, generator=g), torch.randn((B, Hh), device=cuda_device, generator=g)
-    c2, h2 = fused.lstm_pointwise(gates, c)
+    c2, h2 = fused.lstm_pointwise(gates, c, gates2)
     ((c2 * gc).sum() + (h2 * gh).sum()).backward()
-    g64, c64 = gates.detach().double().requires_grad_(True), c.detach().double().requires_grad_(True)
+    total = gates.detach().double() + (gates2.detach().double() if split else 0.0)
+    g64, c64 = total.requires_grad_(True), c.detach().double().requires_grad_(True)
     i, j, f, o = g64.chunk(4, 1)                                   # LSTMCellTF.forward, written out
     rc = torch.sigmoid(f + 1.0) * c64 + torch.sigmoid(i) * torch.tanh(j)
     rh = torch.sigmoid(o) * torch.tanh(rc)
@@ -94,6 +98,8 @@ def test_lstm_pointwise(cuda_device):
     _check(c2, rc, rtol=1e-5, atol=1e-6)
     _check(h2, rh, rtol=1e-5, atol=1e-6)
     _check(gates.grad, g64.grad, rtol=1e-5, atol=1e-6)
+    if split:
+        _check(gates2.grad, g64.grad, rtol=1e-5, atol=1e-6)
     _check(c.grad, c64.grad, rtol=1e-5, atol=1e-6)
 
 
