@@ -87,3 +87,18 @@ def test_batches_are_a_function_of_the_canvas_index_and_feed_the_detection_metri
     scale = whole["size"][:, :, :1].double() / cs
     p, r, g, d, m = detection.detection_metrics(whole["pos"], whole["size"], whole["num"], centre, scale, whole["num"], cs)
     assert float(p[:, 0].min()) == 1.0 and float(r[:, 0].min()) == 1.0 and float(m.min()) > 0.9
+
+
+def test_overlap_rule_mode0_is_the_reference_function():
+    """Parity PINNED for the placement rule: the golden file holds the outputs of the reference's own
+    ``bounding_boxes_overlap`` (tests/golden/make_golden_synth_rule.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "synth_overlap_rule.npz"))
+    got = np.array([S.boxes_clash(0, *[int(v) for v in a], *[int(v) for v in b], int(g)) for a, b, g in zip(z["new"], z["old"], z["gap"])])
+    assert np.array_equal(got, z["overlap"])
+    assert 0.2 < got.mean() < 0.9
+    multi = np.array([any(S.boxes_clash(0, *[int(v) for v in a], *[int(v) for v in q], 1) for q in o)
+                      for a, o in zip(z["multi_new"], z["multi_old"])])
+    assert np.array_equal(multi, z["multi_overlap"])
+    # it is NOT a box-intersection test: boxes in disjoint rows but overlapping columns clash
+    assert S.boxes_clash(0, 10, 0, 5, 5, 10, 40, 5, 5, 0) and not S.boxes_clash(1, 10, 0, 5, 5, 10, 40, 5, 5, 0)
