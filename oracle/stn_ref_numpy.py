@@ -3,11 +3,15 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
 module.  The product path (``mog_asr_b200``) never imports anything from ``oracle/``.
 
-**Parity unpinned**: the reference (taufikxu/MOG-ASR) ships no tests, golden vectors or fixtures for
-this path, and its arithmetic lives in an un-vendored third-party dependency (TensorFlow 1.12.0,
-pinned only by prose in ``README.md:6``) that cannot be installed here (Python 3.12, no index).  This
-file therefore *defines* the evaluation order that TF-1.12 is assumed to use; every assumption is
-flagged ``[TF-1.12 assumed]``.  The CUDA kernels are checked against this definition.
+**Parity unpinned against a live TensorFlow**: the reference (taufikxu/MOG-ASR) ships no tests, golden
+vectors or fixtures for this path, and its arithmetic lives in an un-vendored third-party dependency
+(TensorFlow 1.12.0, pinned only by prose in ``README.md:6``) that cannot be installed here (Python 3.12,
+no index).  This file therefore *defines* the evaluation order that TF-1.12 is assumed to use; every
+assumption is flagged ``[TF-1.12 assumed]``.  The CUDA kernels are checked against this definition.
+**The forward op graph IS pinned**: ``tests/golden/make_golden_graph.py`` executes the reference's own
+``air/transformer.py`` on a numpy stand-in for the TF ops it uses (``tests/golden/tf_shim.py``, same
+per-kernel assumptions) and ``forward`` / ``transformer`` here reproduce its outputs bit for bit
+(``tests/test_oracle.py``).  The closed-form backward (TF autodiff in the reference) has no such anchor.
 
 Line references are to ``/root/reference/air/transformer.py`` unless another file is named.
 

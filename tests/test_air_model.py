@@ -240,3 +240,19 @@ def test_one_step_changes_parameters_like_the_oracle_step(cuda_device):
         assert float(d.max()) <= 2.1e-4
         bad += int((d > 2e-6).sum()); tot += d.numel()
     assert bad <= 1e-3 * tot, (bad, tot)
+
+
+def test_concrete_sample_and_kl_equal_the_reference_source_run_on_the_tf_shim():
+    """``tests/golden/graph_concrete.npz``: the reference's own ``air/concrete.py`` executed in float64 on the numpy TF shim
+    with injected uniform draws.  Pins the graph of the Concrete pre-sigmoid sample (concrete.py:20-27) and of the Monte
+    Carlo KL (:30-64) that ``OracleOps.zpres`` / ``AIRModel._concrete_kl`` restate (and the fused kernels are tested
+    against those in tests/test_air_fused_gpu.py)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_concrete.npz"))
+    lo, prior, u = (torch.tensor(g[k], dtype=torch.float64) for k in ("log_odds", "prior_lo", "u"))
+    for temp in (0.1, 1.0):
+        y, z, _, _, _ = OracleOps().zpres(lo, u, torch.zeros_like(lo), temp, 0.9)
+        np.testing.assert_allclose(y.numpy(), g[f"y_T{temp}"], rtol=1e-12, atol=1e-12)
+        kl = AIRModel._concrete_kl(y, prior, lo, temp)
+        np.testing.assert_allclose(kl.numpy(), g[f"kl_T{temp}"], rtol=1e-10, atol=1e-10)
+        # concrete_binary_sample (:4-17) returns sigmoid(y / T) of the un-divided y: the same z_pres
+        np.testing.assert_allclose(z.numpy(), g[f"sig_T{temp}"], rtol=1e-12, atol=1e-15)

@@ -141,3 +141,31 @@ def test_asr_gating_and_tie_rules():
     np.testing.assert_allclose(r["overlap"], 6 * 15.0, rtol=1e-6)
     # x_diff == y_diff == 0 -> tf.maximum routes to x_diff and abs'(0) = 0: no shift gradient from overlap
     assert np.all(r["d_shifts"] == 0)
+
+
+GRAPH_CASES = ["read_50_28", "write_28_50", "adversarial_17x23x3_9x31", "adversarial_50_28", "adversarial_28_50", "out_1x1", "out_1x7",
+               "fullcover_64_28"]
+
+
+@pytest.mark.parametrize("name", GRAPH_CASES)
+def test_oracle_equals_the_reference_source_run_on_the_tf_shim(name):
+    """``tests/golden/graph_*.npz`` were produced by executing the reference's own ``air/transformer.py`` on a numpy
+    stand-in for the TF ops it uses (``tests/golden/tf_shim.py``, ``make_golden_graph.py``): the op graph -- which corner
+    pairs with which weight, where ``-1.001`` sits, how indices flatten -- is the reference's, only the per-kernel
+    numerics (linspace recurrence, K = 3 accumulation order, add_n order) are the shim's stated assumptions."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g = np.load(os.path.join(here, name + ".npz")), np.load(os.path.join(here, "graph_" + name + ".npz"))
+    rows = g["rows"]
+    out = R.transformer(z["U"][rows], z["theta"][rows], tuple(int(v) for v in z["out_size"]))
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+    assert np.array_equal(z["out"][rows].view(np.uint32), g["out"].view(np.uint32))     # and so is the committed golden output
+
+
+def test_oracle_batch_transformer_equals_the_reference_source_run_on_the_tf_shim():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_batch_transformer.npz"))
+    U, th = g["U"], g["thetas"]
+    nb, nt = th.shape[:2]
+    out = R.transformer(np.repeat(U, nt, axis=0), th.reshape(nb * nt, 6), g["out"].shape[1:3])      # transformer.py:190-194
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))

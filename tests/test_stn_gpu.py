@@ -320,3 +320,25 @@ def test_attention_boxes_match_oracle(cuda_device):
     assert got.shape == ref.shape and np.array_equal(got, ref)
     assert 0 < got[:, :steps].mean() < 0.5          # frames, not filled boxes
     assert np.all(got[:, steps:] == 0.0)            # zero matrices sample the template's centre (= 0) everywhere
+
+
+@pytest.mark.parametrize("name", ["read_50_28", "write_28_50", "adversarial_17x23x3_9x31", "adversarial_50_28", "adversarial_28_50",
+                                  "out_1x1", "out_1x7", "fullcover_64_28"])
+def test_forward_equals_the_reference_source_run_on_the_tf_shim(cuda_device, name):
+    """CUDA forward against ``tests/golden/graph_*.npz``: the outputs of the reference's own ``air/transformer.py``
+    executed on the numpy TF shim (see tests/test_oracle.py) -- bit for bit."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g = np.load(os.path.join(here, name + ".npz")), np.load(os.path.join(here, "graph_" + name + ".npz"))
+    rows = g["rows"]
+    out = M.transformer(torch.tensor(z["U"][rows], device=cuda_device), torch.tensor(z["theta"][rows], device=cuda_device),
+                        tuple(int(v) for v in z["out_size"])).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+
+
+def test_batch_transformer_equals_the_reference_source_run_on_the_tf_shim(cuda_device):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_batch_transformer.npz"))
+    out = M.batch_transformer(torch.tensor(g["U"], device=cuda_device), torch.tensor(g["thetas"], device=cuda_device),
+                              tuple(g["out"].shape[1:3])).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
