@@ -11,7 +11,8 @@ assumption is flagged ``[TF-1.12 assumed]``.  The CUDA kernels are checked again
 **The forward op graph IS pinned**: ``tests/golden/make_golden_graph.py`` executes the reference's own
 ``air/transformer.py`` on a numpy stand-in for the TF ops it uses (``tests/golden/tf_shim.py``, same
 per-kernel assumptions) and ``forward`` / ``transformer`` here reproduce its outputs bit for bit
-(``tests/test_oracle.py``).  The closed-form backward (TF autodiff in the reference) has no such anchor.
+(``tests/test_oracle.py``).  The closed-form backward is checked against ``torch.autograd`` applied to the same reference
+file on a torch-based twin of the shim (``tests/golden/make_golden_graph_grad.py``).
 
 Line references are to ``/root/reference/air/transformer.py`` unless another file is named.
 

@@ -169,3 +169,21 @@ def test_oracle_batch_transformer_equals_the_reference_source_run_on_the_tf_shim
     nb, nt = th.shape[:2]
     out = R.transformer(np.repeat(U, nt, axis=0), th.reshape(nb * nt, 6), g["out"].shape[1:3])      # transformer.py:190-194
     assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+
+
+GRAD_GRAPH_CASES = ["read_50_28", "write_28_50", "adversarial_17x23x3_9x31", "fullcover_64_28", "out_1x7"]
+
+
+@pytest.mark.parametrize("name", GRAD_GRAPH_CASES)
+def test_closed_form_backward_equals_autodiff_of_the_reference_source(name):
+    """``tests/golden/graph_grad_*.npz``: the reference's own ``air/transformer.py`` imported on a torch-based stand-in for
+    its TF ops (``tests/golden/tf_shim_torch.py``) and differentiated by autograd in float32 -- the role TF autodiff plays in
+    the reference (:1098).  The oracle's closed-form backward must agree within the gradient tolerance
+    the CUDA kernels are held to."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g = np.load(os.path.join(here, name + ".npz")), np.load(os.path.join(here, "graph_grad_" + name + ".npz"))
+    rows = g["rows"]
+    assert H.grad_excess(g["dU"], z["dU"][rows], z["absdU"][rows]) <= 1.0
+    assert H.grad_excess(g["dtheta"], z["dtheta"][rows], z["absdtheta"][rows]) <= 1.0
+    assert float(np.abs(g["dU"]).max()) > 0 and float(np.abs(g["dtheta"]).max()) > 0

@@ -342,3 +342,17 @@ def test_batch_transformer_equals_the_reference_source_run_on_the_tf_shim(cuda_d
     out = M.batch_transformer(torch.tensor(g["U"], device=cuda_device), torch.tensor(g["thetas"], device=cuda_device),
                               tuple(g["out"].shape[1:3])).cpu().numpy()
     assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["read_50_28", "write_28_50", "adversarial_17x23x3_9x31", "fullcover_64_28", "out_1x7"])
+def test_backward_matches_autodiff_of_the_reference_source(cuda_device, name):
+    """CUDA gradients against ``tests/golden/graph_grad_*.npz`` (autograd of the reference's own graph on the torch TF shim,
+    float32): both are fp32 evaluations in different summation orders, so each gets half of the tolerance budget around
+    the fp64 closed form -- asserted directly against each other with 2 x GRAD_RTOL."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, g = np.load(os.path.join(here, name + ".npz")), np.load(os.path.join(here, "graph_grad_" + name + ".npz"))
+    rows = g["rows"]
+    _, dU, dth = run_fwd_bwd(cuda_device, z["U"][rows], z["theta"][rows], z["out_size"], z["gout"][rows])
+    assert H.grad_excess(dU, g["dU"], z["absdU"][rows], rtol=2 * H.GRAD_RTOL) <= 1.0
+    assert H.grad_excess(dth, g["dtheta"], z["absdtheta"][rows], rtol=2 * H.GRAD_RTOL) <= 1.0
