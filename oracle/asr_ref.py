@@ -7,9 +7,12 @@ Follows ``/root/reference/air/air_number_bbox_location.py``:
   * out-of-canvas, pairwise size, pairwise overlap ``:1029-1069``
   * how they enter the loss                     ``:1078-1079``
 
-**Parity unpinned**: the reference has no tests; TF-1.12 sub-gradient tie rules are assumed
-([TF-1.12 assumed]): ``maximum(a,b)`` routes the gradient to ``a`` when ``a >= b``; ``abs'(0) = 0``;
-``reduce_min`` splits equally among ties.  torch autograd is steered to the same rules below.
+**Parity pinned to the reference's own lines** (not to a live TensorFlow): ``tests/golden/make_golden_asr_graph.py`` reads
+those lines from the reference file, exec's them on a torch-based stand-in for the TF ops they use and differentiates
+with autograd; ``asr_terms`` reproduces values, logged components and all gradients to 1e-10
+(``tests/test_oracle.py``).  Still assumed ([TF-1.12 assumed]): the sub-gradient tie rules -- ``maximum(a,b)`` routes the
+gradient to ``a`` when ``a >= b``; ``abs'(0) = 0``; ``reduce_min`` splits equally among ties.  torch autograd is steered to
+the same rules below.
 
 Written with torch-CPU ops so autograd provides the gradients (the role TF autodiff plays at ``:1098``).
 """

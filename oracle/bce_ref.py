@@ -2,8 +2,8 @@
 
 Follows ``/root/reference/air/air_number_bbox_location.py:945-968``: clip by ``tf.maximum(tf.minimum(r, 1), 0)``,
 ``log(r + 1e-10)``, row sums; the gradient is what TF autodiff yields ([TF-1.12 assumed] ``minimum``/``maximum``
-route the gradient to their first argument on ties, so both clip bounds pass it).  Parity unpinned (no reference
-tests; see ``stn_ref_numpy.py``)."""
+route the gradient to their first argument on ties, so both clip bounds pass it).  Pinned to the reference's own lines
+exec'd on the torch TF shim (``tests/golden/make_golden_blocks.py``, ``tests/test_oracle.py``); not to a live TensorFlow."""
 import numpy as np
 
 

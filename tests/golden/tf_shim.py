@@ -87,7 +87,7 @@ def tile(x, multiples):
     return _t(np.tile(np.asarray(x), tuple(int(v) for v in np.asarray(multiples).reshape(-1))))
 
 
-def concat(axis, values):
+def concat(values=None, axis=0, **k):
     return _t(np.concatenate([np.asarray(v) for v in values], axis))
 
 

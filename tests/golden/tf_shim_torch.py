@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 _DT = {"float32": torch.float32, "int32": torch.int32, "float64": torch.float64}
+DEFAULT = {"dtype": torch.float32}       # float dtype of constants; a generator may switch it to float64 for a yardstick run
 
 
 def _t(a, dtype=None):
@@ -26,12 +27,12 @@ def _ints(s):
     return tuple(int(v) for v in np.asarray([int(x) for x in s] if isinstance(s, (list, tuple)) else s).reshape(-1))
 
 
-def ones(shape, dtype="float32"):
-    return torch.ones(_ints(shape), dtype=_DT[dtype])
+def ones(shape, dtype=None):
+    return torch.ones(_ints(shape), dtype=_DT[dtype] if dtype else DEFAULT["dtype"])
 
 
-def zeros(shape, dtype="float32"):
-    return torch.zeros(_ints(shape), dtype=_DT[dtype])
+def zeros(shape, dtype=None):
+    return torch.zeros(_ints(shape), dtype=_DT[dtype] if dtype else DEFAULT["dtype"])
 
 
 def ones_like(x):
@@ -70,7 +71,7 @@ def tile(x, multiples):
     return _t(x).repeat(*_ints(multiples))
 
 
-def concat(axis, values):
+def concat(values=None, axis=0, **k):
     return torch.cat([_t(v) for v in values], axis)
 
 
@@ -116,3 +117,82 @@ def matmul(a, b):
 
 def Variable(initial_value=None, **k):
     return _t(initial_value)
+
+
+# ---- the additional ops of the ASR regulariser block (air_number_bbox_location.py:645-681, :970-1069) ------------------
+float32 = "float32"
+
+
+def convert_to_tensor(x, dtype=None):
+    return torch.as_tensor(np.asarray(x), dtype=DEFAULT["dtype"])
+
+
+def reduce_mean(x, axis=None):
+    return x.mean() if axis is None else x.mean(axis)
+
+
+def reduce_sum(x, axis=None, name=None):
+    return x.sum() if axis is None else x.sum(axis)
+
+
+def reduce_min(x, axis=None):
+    return torch.amin(x, dim=axis)                      # ties share the gradient equally, like TF's reduce_min
+
+
+def log(x):
+    return torch.log(x)
+
+
+def maximum(x, y, name=None):
+    y = _t(y).to(x.dtype) if not isinstance(y, torch.Tensor) else y
+    return torch.where(x >= y, x, y)                    # TF: gradient to x where x >= y, to y elsewhere [TF-1.12 assumed]
+
+
+def minimum(x, y, name=None):
+    y = _t(y).to(x.dtype) if not isinstance(y, torch.Tensor) else y
+    return torch.where(x <= y, x, y)                    # TF: gradient to x where x <= y [TF-1.12 assumed]
+
+
+def square(x):
+    return x * x
+
+
+def abs(x):  # noqa: A001
+    return torch.abs(x)
+
+
+def zeros_like(x):
+    return torch.zeros_like(x)
+
+
+def eye(n):
+    return torch.eye(int(n), dtype=DEFAULT["dtype"])
+
+
+class nn:  # noqa: N801
+    @staticmethod
+    def sigmoid(x):
+        return torch.sigmoid(x)
+
+    @staticmethod
+    def softplus(x):
+        return torch.nn.functional.softplus(x)
+
+    @staticmethod
+    def sigmoid_cross_entropy_with_logits(labels=None, logits=None):
+        # TF's documented formulation: max(x, 0) - x * z + log(1 + exp(-|x|))
+        x, z = logits, labels
+        return torch.where(x >= 0, x, torch.zeros_like(x)) - x * z + torch.log1p(torch.exp(-torch.abs(x)))
+
+
+class layers:  # noqa: N801
+    @staticmethod
+    def flatten(x):
+        return x.reshape(x.shape[0], -1)
+
+
+_tile_plain = tile
+
+
+def tile(x, multiples):  # noqa: F811  (multiples may hold a 0-d tensor, e.g. self.batch_size)
+    return _tile_plain(x, [int(m) for m in multiples])

@@ -256,3 +256,20 @@ def test_fused_mean_logvar_pair_matches_framework_ops(cuda_device):
     flat = lambda o: [t for step in o for t in step]
     for a, b in zip(flat(o0) + g0 + p0, flat(o1) + g1 + p1):
         assert float((a - b).abs().max()) <= 3e-5 * max(1.0, float(a.abs().max()))
+
+
+def test_thetas_kernel_vs_the_reference_source_run_on_the_tf_shim(cuda_device):
+    """Directly against ``tests/golden/graph_thetas.npz`` (the reference's st_forward / st_backward lines on the torch TF
+    shim, float32): both matrices bit for bit, gradients to rounding."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_thetas.npz"))
+    s = torch.tensor(g["s"][:, None], device=cuda_device, requires_grad=True)
+    xy = torch.tensor(np.stack([g["x"], g["y"]], 1), device=cuda_device, requires_grad=True)
+    th_r, th_w = fused.thetas(xy, s)
+    assert np.array_equal(th_r.detach().cpu().numpy().reshape(-1, 2, 3).view(np.uint32), g["theta"].view(np.uint32))
+    assert np.array_equal(th_w.detach().cpu().numpy().reshape(-1, 2, 3).view(np.uint32), g["theta_recon"].view(np.uint32))
+    ((th_r.reshape(-1, 2, 3) * torch.tensor(g["wr"], device=cuda_device)).sum()
+     + (th_w.reshape(-1, 2, 3) * torch.tensor(g["ww"], device=cuda_device)).sum()).backward()
+    np.testing.assert_allclose(s.grad.cpu().numpy()[:, 0], g["ds"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(xy.grad.cpu().numpy()[:, 0], g["dx"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(xy.grad.cpu().numpy()[:, 1], g["dy"], rtol=2e-5, atol=1e-5)

@@ -66,3 +66,29 @@ def test_asr_c3_batch_256_seeded(cuda_device):
     close(t[1].grad.cpu().numpy(), ref["d_shifts"], GRAD_RTOL, "d_shifts")
     close(t[2].grad.cpu().numpy()[..., 0], ref["d_scales"], GRAD_RTOL, "d_scales")
     assert float(margin.detach()) == 0.0 and torch.all(t[0].grad == 0)
+
+
+@pytest.mark.parametrize("name", [f"graph_asr_{c}_T{t}" for c in ("c2", "c3", "all") for t in (6, 3)])
+def test_asr_kernel_vs_the_reference_source_run_on_the_tf_shim(cuda_device, name):
+    """The fused kernel directly against ``tests/golden/graph_asr_*.npz`` -- the reference's own regulariser lines exec'd on
+    the torch TF shim in float64 (tests/golden/make_golden_asr_graph.py); loss = mean(per_image) + margin (:1078-1079)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = {str(k): eval(str(v), {"__builtins__": {}}) for k, v in zip(g["cfg_keys"], g["cfg_vals"])}
+    reg = M.AsrRegulariser(canvas_size=cfg["canvas_size"], max_steps=cfg["max_steps"], constrains_num=cfg["counts"],
+                           constrains_num_gamma=cfg["gn"], constrains_margin_gamma=cfg["gm"], constrains_num_element_gamma=cfg["gne"],
+                           constrains_bbox_gamma=cfg["gb"], constrains_sharesize_gamma=cfg["gs"], constrains_area_gamma=cfg["ga"],
+                           constrains_area_minmax=cfg["minmax"])
+    dev = cuda_device
+    lo = torch.tensor(g["log_odds"], dtype=torch.float32, device=dev, requires_grad=True)
+    sh = torch.tensor(g["shifts"], dtype=torch.float32, device=dev, requires_grad=True)
+    sc = torch.tensor(g["scales"], dtype=torch.float32, device=dev, requires_grad=True)
+    per_image, margin, comps = M.asr_regularisers(reg, lo, sh, sc)
+    close(per_image.detach().cpu().numpy(), g["per_image"], VAL_RTOL, "per_image")
+    close(margin.detach().cpu().numpy(), g["margin"], VAL_RTOL, "margin")
+    for i, k in ((2, "area"), (3, "out_loss"), (4, "size"), (5, "overlap")):
+        close(comps[:, i].cpu().numpy(), g[k], VAL_RTOL, k)
+    (per_image.mean() + margin).backward()
+    close(lo.grad.cpu().numpy() if lo.grad is not None else np.zeros_like(g["d_log_odds"]), g["d_log_odds"], GRAD_RTOL, "d_log_odds")
+    close(sh.grad.cpu().numpy(), g["d_shifts"], GRAD_RTOL, "d_shifts")
+    close(sc.grad.cpu().numpy(), g["d_scales"], GRAD_RTOL, "d_scales")

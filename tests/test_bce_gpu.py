@@ -46,3 +46,27 @@ def test_bce_matches_reference_ops_on_device(cuda_device):
     r = torch.clamp(c.detach(), 0, 1)
     ref = -(x * torch.log(r + 1e-10) + (1 - x) * torch.log(1 - r + 1e-10)).sum(1)
     assert torch.allclose(loss, ref, rtol=1e-5)
+
+
+def test_bce_kernel_vs_the_reference_source_run_on_the_tf_shim(cuda_device):
+    """Directly against ``tests/golden/graph_recon.npz`` (the reference's own lines :944-967 on the torch TF shim, float64)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_recon.npz"))
+    c32, x32 = g["canvas"].astype(np.float32), g["images"].astype(np.float32)
+    ct = torch.tensor(c32, device=cuda_device, requires_grad=True)
+    loss, mse = reconstruction_loss(ct, torch.tensor(x32, device=cuda_device))
+    loss.backward(torch.tensor(g["w"].astype(np.float32), device=cuda_device))
+    # the golden inputs are float64; evaluate the oracle (itself pinned to the golden file on the CPU) on the fp32-rounded inputs
+    ref_loss, ref_mse = bce_ref.reconstruction_loss(c32, x32)
+    mag = bce_ref.term_magnitudes(c32, x32)
+    assert np.all(np.abs(loss.detach().cpu().numpy() - ref_loss) <= 2e-6 * mag + 1e-12)
+    assert np.all(np.abs(ref_loss - g["loss"]) <= 1e-5 * mag)                 # fp32 rounding of the inputs only
+    np.testing.assert_allclose(mse.cpu().numpy(), ref_mse, rtol=2e-6, atol=1e-12)
+    d = ct.grad.cpu().numpy()
+    passes = (c32 >= 0) & (c32 <= 1)
+    assert np.all(d[~passes] == 0)
+    ref_d = bce_ref.reconstruction_loss_backward(c32, x32, g["w"].astype(np.float32))
+    r = np.clip(c32.astype(np.float64), 0, 1)
+    dmag = (np.abs(x32 / (r + 1e-10)) + np.abs((1 - x32) / (1 - r + 1e-10))) * np.abs(g["w"].astype(np.float32))[:, None]
+    assert np.all(np.abs(d - ref_d) <= 2e-6 * dmag + 1e-30)
+    assert np.abs(d).max() > 1e9

@@ -187,3 +187,58 @@ def test_closed_form_backward_equals_autodiff_of_the_reference_source(name):
     assert H.grad_excess(g["dU"], z["dU"][rows], z["absdU"][rows]) <= 1.0
     assert H.grad_excess(g["dtheta"], z["dtheta"][rows], z["absdtheta"][rows]) <= 1.0
     assert float(np.abs(g["dU"]).max()) > 0 and float(np.abs(g["dtheta"]).max()) > 0
+
+
+@pytest.mark.parametrize("name", [f"graph_asr_{c}_T{t}" for c in ("c2", "c3", "all") for t in (6, 3)])
+def test_asr_oracle_equals_the_reference_source_run_on_the_tf_shim(name):
+    """``tests/golden/graph_asr_*.npz``: the reference's own regulariser lines (air_number_bbox_location.py:645-678 and
+    :970-1069) exec'd on the torch-based TF shim in float64 and differentiated by autograd
+    (``tests/golden/make_golden_asr_graph.py``).  ``oracle/asr_ref.py`` must reproduce values, logged components and all
+    three gradients of ``reduce_mean(pr_loss + num_element_min) + num_marginal_loss`` (:1078-1079)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = {str(k): eval(str(v), {"__builtins__": {}}) for k, v in zip(g["cfg_keys"], g["cfg_vals"])}
+    r = asr_ref.asr_numpy(g["log_odds"], g["shifts"], g["scales"][..., 0], canvas_size=cfg["canvas_size"], counts=cfg["counts"],
+                          max_steps=cfg["max_steps"], gamma_num=cfg["gn"], gamma_margin=cfg["gm"], gamma_elem=cfg["gne"],
+                          gamma_bbox=cfg["gb"], gamma_size=cfg["gs"], gamma_area=cfg["ga"], area_minmax=cfg["minmax"])
+    tol = dict(rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(r["per_image"], g["per_image"], **tol)
+    np.testing.assert_allclose(r["margin"], g["margin"], **tol)
+    for mine, theirs in (("area", "area"), ("out", "out_loss"), ("size", "size"), ("overlap", "overlap")):
+        np.testing.assert_allclose(r[mine], g[theirs], **tol)
+    np.testing.assert_allclose(r["per_image"].mean() + r["margin"], g["loss"], **tol)
+    np.testing.assert_allclose(r["d_log_odds"], g["d_log_odds"], **tol)
+    np.testing.assert_allclose(r["d_shifts"], g["d_shifts"], **tol)
+    np.testing.assert_allclose(r["d_scales"], g["d_scales"][..., 0], **tol)
+
+
+def test_recon_loss_oracle_equals_the_reference_source_run_on_the_tf_shim():
+    """``tests/golden/graph_recon.npz``: the reference's own reconstruction-loss lines (:944-967) exec'd on the torch-based
+    TF shim in float64 (clip bounds hit exactly, sums above 1, zero pixels under objects included), gradient by autograd."""
+    import os
+    from oracle import bce_ref
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_recon.npz"))
+    loss, mse = bce_ref.reconstruction_loss(g["canvas"], g["images"])
+    np.testing.assert_allclose(loss, g["loss"], rtol=1e-12)
+    np.testing.assert_allclose(mse, g["mse"], rtol=1e-12)
+    d = bce_ref.reconstruction_loss_backward(g["canvas"], g["images"], g["w"])
+    np.testing.assert_allclose(d, g["dcanvas"], rtol=1e-12, atol=1e-12)
+    assert np.abs(g["dcanvas"]).max() > 1e9          # the 1e10 slopes at canvas == 0 are part of the reference
+
+
+def test_theta_construction_equals_the_reference_source_run_on_the_tf_shim():
+    """``tests/golden/graph_thetas.npz``: the ``st_forward`` / ``st_backward`` lines (:511-531, :563-584) exec'd on the shim in
+    float32: ``OracleOps.thetas`` reproduces both matrices bit for bit and their gradients to rounding."""
+    import os
+    import torch
+    from oracle.air_ops import OracleOps
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_thetas.npz"))
+    s = torch.tensor(g["s"], requires_grad=True)
+    xy = torch.tensor(np.stack([g["x"], g["y"]], 1), requires_grad=True)
+    th_r, th_w = OracleOps().thetas(xy, s[:, None])
+    assert np.array_equal(th_r.detach().numpy().reshape(-1, 2, 3).view(np.uint32), g["theta"].view(np.uint32))
+    assert np.array_equal(th_w.detach().numpy().reshape(-1, 2, 3).view(np.uint32), g["theta_recon"].view(np.uint32))
+    ((th_r.reshape(-1, 2, 3) * torch.tensor(g["wr"])).sum() + (th_w.reshape(-1, 2, 3) * torch.tensor(g["ww"])).sum()).backward()
+    np.testing.assert_allclose(s.grad.numpy(), g["ds"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(xy.grad.numpy()[:, 0], g["dx"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(xy.grad.numpy()[:, 1], g["dy"], rtol=2e-5, atol=1e-5)
