@@ -140,7 +140,7 @@ def reduce_min(x, axis=None):
 
 
 def log(x):
-    return torch.log(x)
+    return torch.log(x if isinstance(x, torch.Tensor) else torch.tensor(x, dtype=DEFAULT["dtype"]))
 
 
 def maximum(x, y, name=None):
@@ -196,3 +196,41 @@ _tile_plain = tile
 
 def tile(x, multiples):  # noqa: F811  (multiples may hold a 0-d tensor, e.g. self.batch_size)
     return _tile_plain(x, [int(m) for m in multiples])
+
+
+# ---- the additional ops of the loop-body KL / stopping / canvas lines (air_number_bbox_location.py:683-787) ---------------
+int32 = "int32"
+
+
+def where(cond, a, b):
+    # TF 1.x tf.where: a rank-1 condition selects whole ROWS of higher-rank operands
+    while cond.dim() < a.dim():
+        cond = cond.unsqueeze(-1)
+    return torch.where(cond, a, b)
+
+
+def less(a, b):
+    return a < b
+
+
+def exp(x):
+    return torch.exp(x)
+
+
+def reduce_logsumexp(x, axis=None):
+    return torch.logsumexp(x, dim=axis)
+
+
+class TensorArray:
+    """the two methods the loop body uses: ``ta = ta.write(ta.size(), value)``"""
+
+    def __init__(self):
+        self.items = []
+
+    def size(self):
+        return len(self.items)
+
+    def write(self, index, value):
+        assert index == len(self.items)
+        self.items.append(value)
+        return self

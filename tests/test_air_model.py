@@ -256,3 +256,48 @@ def test_concrete_sample_and_kl_equal_the_reference_source_run_on_the_tf_shim():
         np.testing.assert_allclose(kl.numpy(), g[f"kl_T{temp}"], rtol=1e-10, atol=1e-10)
         # concrete_binary_sample (:4-17) returns sigmoid(y / T) of the un-divided y: the same z_pres
         np.testing.assert_allclose(z.numpy(), g[f"sig_T{temp}"], rtol=1e-12, atol=1e-15)
+
+
+def test_loop_body_kl_masks_and_canvas_equal_the_reference_source_run_on_the_tf_shim():
+    """``tests/golden/graph_loop_kl.npz``: lines :683-787 of the reference's loop body exec'd per step on the torch TF shim in
+    float64 (``tests/golden/make_golden_loop_kl.py``).  The model's restatement must give the same per-step KL arrays (the
+    z_pres term masked by the PREVIOUS stopping sum, the others and the canvas write by the UPDATED one), the same digit
+    counts, stopping sums and canvas, and the same gradients of a weighted sum of the KL part of the ELBO and the canvas."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_loop_kl.npz"))
+    cv = dict(zip([str(k) for k in g["cfg_keys"]], g["cfg_vals"]))
+    cfg = config_from_flags("mnist", "13", zt=float(cv["z_pres_temperature"]))
+    assert (cfg.stopping_threshold, cfg.scale_prior_mean, cfg.scale_prior_variance, cfg.vae_prior_mean, cfg.vae_prior_variance) == \
+        tuple(float(cv[k]) for k in ("stopping_threshold", "scale_prior_mean", "scale_prior_variance", "vae_prior_mean", "vae_prior_variance"))
+    model, ops = AIRModel(cfg, ops=OracleOps()), OracleOps()
+    keys = ("y", "prior_lo", "post_lo", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "g_sh_mean", "g_sh_lv", "v_mean", "v_lv", "window")
+    t = {k: torch.tensor(g[k], dtype=torch.float64, requires_grad=True) for k in keys}
+    T, B = g["y"].shape
+    cs = int(cv["canvas_size"])
+    stop, canvas = torch.zeros(B, dtype=torch.float64), torch.zeros(B, cs * cs, dtype=torch.float64)
+    digits = torch.zeros(B, dtype=torch.int32)
+    kls = {k: [] for k in ("z_pres_kl", "scale_kl", "shift_kl", "vae_kl")}
+    for s in range(T):
+        z = torch.sigmoid(t["y"][s])
+        active_prev = stop < cfg.stopping_threshold
+        stop = stop + (1.0 - z)                                                                   # OracleOps.zpres, written out
+        active = stop < cfg.stopping_threshold
+        digits = digits + active.to(torch.int32)
+        canvas = canvas + torch.where(active[:, None], z[:, None] * t["window"][s].reshape(B, -1), torch.zeros_like(canvas))
+        zk = AIRModel._concrete_kl(t["y"][s], t["prior_lo"][s], t["post_lo"][s], cfg.z_pres_temperature)
+        sk, hk, vk = model._gaussian_kls(t["sc_mean"][s], t["sc_lv"][s], t["sh_mean"][s], t["sh_lv"][s], t["g_sh_mean"][s],
+                                         t["g_sh_lv"][s], t["v_mean"][s], t["v_lv"][s])
+        kls["z_pres_kl"].append(torch.where(active_prev, zk, torch.zeros_like(zk)))
+        for k, v in (("scale_kl", sk), ("shift_kl", hk), ("vae_kl", vk)):
+            kls[k].append(torch.where(active, v, torch.zeros_like(v)))
+    tol = dict(rtol=1e-10, atol=1e-10)
+    for k, v in kls.items():
+        np.testing.assert_allclose(torch.stack(v, 0).detach().numpy(), g["kl_" + k], **tol)
+    np.testing.assert_allclose(stop.detach().numpy(), g["stop_sum"], **tol)
+    assert np.array_equal(digits.numpy(), g["digits"])
+    np.testing.assert_allclose(canvas.detach().numpy(), g["canvas"], **tol)
+    elbo_kl = sum(torch.stack(v, 0).sum(0) for v in kls.values())
+    np.testing.assert_allclose(elbo_kl.detach().numpy(), g["elbo_kl"], **tol)
+    ((elbo_kl * torch.tensor(g["w"])).sum() + (canvas * torch.tensor(g["wc"])).sum()).backward()
+    for k in keys:
+        got = t[k].grad.numpy() if t[k].grad is not None else np.zeros_like(g[k])
+        np.testing.assert_allclose(got, g["d_" + k], rtol=1e-9, atol=1e-9, err_msg=k)
