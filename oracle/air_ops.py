@@ -2,7 +2,9 @@
 three hot-path operators are the oracle's torch restatements (``oracle/stn_ref_torch.py``,
 ``oracle/asr_ref.py``) and plain reference ops for the composite (``air/air_number_bbox_location.py:722-727``).
 Used by tests/ (parity of the training step) and by bench.py's CPU-baseline leg; the product never imports it.
-Parity unpinned (see ``stn_ref_numpy.py``)."""
+Pinned to the reference's own graph (not to a live TensorFlow): the re-hosted model driven by these operators reproduces the
+reference's ``AIRModel._create_model`` executed on the torch TF shim -- loss, loop trip count, counts, canvas and every weight
+gradient (``tests/golden/make_golden_model.py``, ``tests/test_air_model.py``)."""
 import torch
 import torch.distributed as dist
 

@@ -301,3 +301,68 @@ def test_loop_body_kl_masks_and_canvas_equal_the_reference_source_run_on_the_tf_
     for k in keys:
         got = t[k].grad.numpy() if t[k].grad is not None else np.zeros_like(g[k])
         np.testing.assert_allclose(got, g["d_" + k], rtol=1e-9, atol=1e-9, err_msg=k)
+
+
+def _load_reference_graph_run(name):
+    """weights / noise / outputs of the reference's whole training graph executed on the torch TF shim
+    (tests/golden/make_golden_model.py) and the matching re-hosted model with those weights loaded"""
+    from mog_asr_b200.air.model import AIRConfig
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"graph_model_{name}.npz"))
+    c = eval(str(g["cfg"]), {"__builtins__": {}})
+    cfg = AIRConfig(canvas_size=c["canvas"], windows_size=c["ws"], max_steps=c["max_steps"], rnn_units=c["rnn"], vae_latent_dimensions=c["lat"],
+                    vae_recognition_units=c["rec"], vae_generative_units=c["gen"], scale_hidden_units=c["hid"], shift_hidden_units=c["hid"],
+                    z_pres_hidden_units=c["hid"], z_pres_temperature=c["zt"], constrains_num=c["counts"], constrains_num_gamma=c["gn"],
+                    constrains_margin_gamma=c["gm"], constrains_num_element_gamma=c["gne"], constrains_bbox_gamma=c["gb"],
+                    constrains_sharesize_gamma=c["gs"], constrains_area_gamma=c["ga"], constrains_area_minmax=tuple(c["minmax"]),
+                    fix_steps=c["counts"][0] if len(c["counts"]) == 1 else None)
+    model = AIRModel(cfg, ops=OracleOps()).double()
+    P = "air/air_model/"                                           # TF variable names -> parameters (dense kernels are [in, out])
+    dense = lambda tfname, lyr, w="kernel", b="bias": {lyr + ".weight": (P + tfname + "/" + w, True), lyr + ".bias": (P + tfname + "/" + b, False)}
+    mp = {"infer_cell.kernel": (P + "infer_rnn_running/lstm_cell/kernel", False), "infer_cell.bias": (P + "infer_rnn_running/lstm_cell/bias", False),
+          "gen_cell.kernel": (P + "gen_rnn_running/lstm_cell/kernel", False), "gen_cell.bias": (P + "gen_rnn_running/lstm_cell/bias", False)}
+    for head in ("inf_shift", "inf_scale", "gen_shift"):           # hidden_m, mean, hidden_v, log-variance: the order the reference creates them
+        for tfl, mine in (("dense", "hm"), ("dense_1", "m"), ("dense_2", "hv"), ("dense_3", "v")):
+            mp.update(dense(f"{head}/{tfl}", f"{head}.{mine}"))
+    for i in (1, 2):
+        mp.update(dense(f"vae/recognition_{i}", f"vae_rec.{i - 1}", "weights", "biases"))
+        mp.update(dense(f"vae/generative_{i}", f"vae_gen.{i - 1}", "weights", "biases"))
+    for tfl, mine in (("rec_mean", "vae_rec_mean"), ("rec_log_variance", "vae_rec_logvar"), ("gen_mean", "vae_gen_mean")):
+        mp.update(dense("vae/" + tfl, mine, "weights", "biases"))
+    mp.update(dense("z_pres/log_odds/dense", "z_post_h")); mp.update(dense("z_pres/log_odds/dense_1", "z_post"))
+    if cfg.fix_steps is None:
+        mp.update(dense("z_pres/prior/dense", "z_prior_h")); mp.update(dense("z_pres/prior/dense_1", "z_prior"))
+    params = dict(model.named_parameters())
+    assert set(params) == set(mp) and len([k for k in g.files if k.startswith("w:")]) == len(mp)     # same variables, nothing left over
+    with torch.no_grad():
+        for n, (tfn, tr) in mp.items():
+            w = torch.tensor(g["w:" + tfn])
+            params[n].copy_(w.t() if tr else w)
+    return g, cfg, model, params, mp
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_rehosted_model_equals_the_reference_graph_run_on_the_tf_shim(name):
+    """The reference's WHOLE training graph (``AIRModel._create_model`` with its own vae / concrete / transformer files) was
+    executed on the torch TF shim in float64 with seeded weights and injected noise (``tests/golden/make_golden_model.py``;
+    regulariser flags of BASELINE configs 2 and 3, shrunken layer widths).  The re-hosted model with the same weights and
+    noise must run the same number of loop iterations (the data-dependent ``while`` condition), infer the same counts and
+    reproduce the loss, the per-image terms, the canvas and the gradient of the loss w.r.t. every weight.  Library layers
+    (dense, LSTMCell) are the shim's definition; what is pinned is the wiring of the whole step."""
+    g, cfg, model, params, mp = _load_reference_graph_run(name)
+    noise = lambda kind, step, shape: torch.tensor(g["noise_" + kind][step]).reshape(shape)
+    out = model(torch.tensor(g["images"]), noise=noise)
+    out["loss"].backward()
+    assert out["steps"] == int(g["steps"]) and out["steps"] < cfg.max_steps            # the loop really stopped early
+    assert np.array_equal(out["rec_num_digits"].numpy(), g["rec_num_digits"])
+    np.testing.assert_allclose(float(out["loss"].detach()), float(g["loss"]), rtol=1e-8)
+    np.testing.assert_allclose(float(out["margin"]), float(g["margin"]), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(out["rec_scales"].numpy(), g["rec_scales"], atol=1e-8)
+    np.testing.assert_allclose(out["rec_shifts"].numpy(), g["rec_shifts"], atol=1e-8)
+    np.testing.assert_allclose(out["z_pres_probs"].numpy(), g["z_pres_probs"], atol=1e-8)
+    np.testing.assert_allclose(out["reconstruction"].numpy(), g["reconstruction"], atol=2e-6)    # fp32-rounded sampler constants
+    np.testing.assert_allclose(out["recon"].numpy(), g["recon_loss"], rtol=1e-7)
+    for n, (tfn, tr) in mp.items():
+        ref = torch.tensor(g["g:" + tfn])
+        ref = ref.t() if tr else ref
+        assert float(ref.abs().max()) > 0, n                                                        # every weight is live in the graph
+        assert float((params[n].grad - ref).abs().max()) <= 3e-4 * float(ref.abs().max()), n
