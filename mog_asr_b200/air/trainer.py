@@ -86,18 +86,22 @@ class Trainer:
         if self.pg is not None and self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
 
+    def clean_and_clip(self):
+        """:1100-1111: per variable ``inf -> 0``, ``nan -> 0``, then ``tf.clip_by_norm(g, gradient_clipping_norm)``
+        (``g * clip / max(||g||, clip)``); only when a clipping norm is configured, like the reference."""
+        c = self.cfg.gradient_clipping_norm
+        if c is None:
+            return
+        torch.nan_to_num_(self.flat_grad, nan=0.0, posinf=0.0, neginf=0.0)
+        norms = torch.stack(torch._foreach_norm(self.grads))           # all 50 scales in three small kernels
+        scales = c / torch.clamp(norms, min=c)
+        torch._foreach_mul_(self.grads, list(scales.unbind(0)))
+
     def postprocess_and_apply(self):
         """:1100-1111 per-variable inf/nan -> 0 and clip_by_norm, then TF's Adam update
         ``lr_t = lr*sqrt(1-b2^t)/(1-b1^t); var -= lr_t * m / (sqrt(v) + eps)``.  The step counter lives on the
         device so the whole update is CUDA-graph capturable."""
-        g = self.flat_grad
-        torch.nan_to_num_(g, nan=0.0, posinf=0.0, neginf=0.0)
-        c = self.cfg.gradient_clipping_norm
-        if c is not None:
-            # tf.clip_by_norm per variable: g * clip / max(norm, clip)  -- all 50 scales in three small kernels
-            norms = torch.stack(torch._foreach_norm(self.grads))
-            scales = c / torch.clamp(norms, min=c)
-            torch._foreach_mul_(self.grads, list(scales.unbind(0)))
+        self.clean_and_clip()
         self.t += 1
         b1, b2 = self.beta1, self.beta2
         self.t_dev += 1.0

@@ -234,3 +234,17 @@ class TensorArray:
         assert index == len(self.items)
         self.items.append(value)
         return self
+
+
+# ---- gradient post-processing (air_number_bbox_location.py:1100-1111) ------------------------------------------------------
+def is_inf(x):
+    return torch.isinf(x)
+
+
+def is_nan(x):
+    return torch.isnan(x)
+
+
+def clip_by_norm(t, clip_norm):
+    # TF: t * clip_norm / max(||t||_2, clip_norm)  [TF-1.12 assumed]
+    return t * clip_norm / torch.clamp(torch.sqrt((t * t).sum()), min=clip_norm)

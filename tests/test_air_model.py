@@ -398,3 +398,26 @@ def test_cuda_model_forward_equals_the_reference_graph_run_on_the_tf_shim(name, 
     print("fp32 product path vs float64 reference graph:", dev)
     limits = dict(scales=2e-6, shifts=2e-6, probs=2e-6, canvas=1e-4, reg=1e-4, margin=1e-5)
     assert all(dev[k] <= limits[k] for k in limits), dev
+
+
+def test_gradient_cleaning_and_clipping_equal_the_reference_lines():
+    """``tests/golden/graph_gradpost.npz``: lines :1100-1111 of the reference (inf -> 0, nan -> 0, per-variable clip_by_norm)
+    exec'd on the torch TF shim for gradients holding infinities, NaNs, large and small norms."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_gradpost.npz"))
+    tr = Trainer(config_from_flags("mnist", "13"), "cpu", ops=OracleOps())
+    n = len([k for k in g.files if k.startswith("in")])
+    assert tr.cfg.gradient_clipping_norm == float(g["clip"])
+    tr.flat_grad.zero_()
+    used = []
+    for k in range(n):                                   # drop each golden gradient into a variable's slot that is large enough
+        src = torch.tensor(g[f"in{k}"]).reshape(-1)
+        slot = next(i for i, v in enumerate(tr.grads) if v.numel() >= src.numel() and i not in used)
+        used.append(slot)
+        tr.grads[slot].reshape(-1)[:src.numel()] = src
+    tr.clean_and_clip()
+    for k, slot in enumerate(used):
+        want = g[f"out{k}"].reshape(-1)
+        got = tr.grads[slot].reshape(-1)[:want.size].numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-12)
+        assert np.all(tr.grads[slot].reshape(-1)[want.size:].numpy() == 0)
+    assert torch.isfinite(tr.flat_grad).all()
