@@ -28,6 +28,7 @@ CONFIGS = {
     # widths are shrunk (the wiring does not depend on them) so that weights + gradients stay ~1 MB per file
     "c2": (20, [1, 3], 0.0, 100.0, 10.0, 0.0, 0.0, 0.0, [7.0, 9.0], 0.1),        # -dn 13 -gm 100 -gne 10
     "c3": (24, [3], 0.0, 0.0, 0.0, 1.0, 10.0, 20.0, [5.0, 6.0], 0.1),            # -dn 3 -ds bbox20k -gb 1 -gs 10 -ga 20 (fix_steps = 3)
+    "all": (22, [1, 2, 4], 0.7, 3.0, 2.0, 1.5, 0.5, 0.25, [6.0, 8.0], 1.0),      # every regulariser on, temperature 1
 }
 MAX_STEPS, B = 6, 5
 WS, RNN, LAT, REC, GEN, HID = 12, 32, 8, (40, 24), (24, 40), 16

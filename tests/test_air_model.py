@@ -340,7 +340,7 @@ def _load_reference_graph_run(name):
     return g, cfg, model, params, mp
 
 
-@pytest.mark.parametrize("name", ["c2", "c3"])
+@pytest.mark.parametrize("name", ["c2", "c3", "all"])
 def test_rehosted_model_equals_the_reference_graph_run_on_the_tf_shim(name):
     """The reference's WHOLE training graph (``AIRModel._create_model`` with its own vae / concrete / transformer files) was
     executed on the torch TF shim in float64 with seeded weights and injected noise (``tests/golden/make_golden_model.py``;
@@ -352,7 +352,7 @@ def test_rehosted_model_equals_the_reference_graph_run_on_the_tf_shim(name):
     noise = lambda kind, step, shape: torch.tensor(g["noise_" + kind][step]).reshape(shape)
     out = model(torch.tensor(g["images"]), noise=noise)
     out["loss"].backward()
-    assert out["steps"] == int(g["steps"]) and out["steps"] < cfg.max_steps            # the loop really stopped early
+    assert out["steps"] == int(g["steps"]) and (name == "all" or out["steps"] < cfg.max_steps)   # c2 / c3: the loop really stopped early
     assert np.array_equal(out["rec_num_digits"].numpy(), g["rec_num_digits"])
     np.testing.assert_allclose(float(out["loss"].detach()), float(g["loss"]), rtol=1e-8)
     np.testing.assert_allclose(float(out["margin"]), float(g["margin"]), rtol=1e-9, atol=1e-12)
