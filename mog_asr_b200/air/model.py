@@ -294,8 +294,11 @@ class _MeanVar(nn.Module):
 
     # ---- fused form (csrc/mog_air_head.cu): one library GEMM + one kernel each way ----------------------------------
     def fusable(self, ops, x):
-        return (getattr(ops, "fused_heads", False) and self.hm.defer and x.is_cuda and x.dtype == torch.float32
-                and self.hm.weight.shape[0] in (16, 32, 64, 128) and self.m.weight.shape[0] <= 2 and self.skip_dim <= 2)
+        # (only inside a training step: the concatenated first-layer weight is rebuilt by prepare() at the start of every
+        #  differentiated forward pass and would be stale in a later no-grad evaluation)
+        return (getattr(ops, "fused_heads", False) and self.hm.defer and torch.is_grad_enabled() and x.is_cuda
+                and x.dtype == torch.float32 and self.hm.weight.shape[0] in (16, 32, 64, 128) and self.m.weight.shape[0] <= 2
+                and self.skip_dim <= 2)
 
     def prepare(self):
         """[W1m | W1v] without the skip columns, rebuilt once per training step (the weights change every step)"""
