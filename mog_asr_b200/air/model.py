@@ -461,12 +461,15 @@ class AIRModel(nn.Module):
 
     # ---- the training graph ----------------------------------------------------------------------------------
     def forward(self, images, noise: Optional[Callable] = None, any_reduce: Optional[Callable] = None,
-                global_batch: Optional[int] = None, recon_loss_fn: Optional[Callable] = None):
+                global_batch: Optional[int] = None, recon_loss_fn: Optional[Callable] = None, train: bool = True):
         """images ``[B, cs*cs]`` in [0,1].  ``noise(kind, step, shape)`` supplies N(0,1) ('shift','scale','vae')
         or U(0,1) ('concrete') draws.  ``any_reduce(flag_tensor)`` makes the loop condition global across ranks.
         ``recon_loss_fn(images, clipped_canvas) -> [B]`` replaces the reference's cross-entropy (:954-959); it
         exists for tests only: the reference term has gradients of 1e10 wherever the canvas is exactly 0 under
         an object pixel, which amplifies fp32 rounding noise of *any* implementation beyond comparison.
+        ``train=False`` is the reference's test model (``train_air_pr.py:170-171``): z_pres is rounded to 0/1 right after
+        the sigmoid (:634-635), so the stopping sum, the counts and the canvas are those of hard decisions; run it under
+        ``torch.no_grad()`` -- this is what feeds ``detection.evaluation``.
         Returns a dict with ``loss`` (differentiable) and the reference's log variables."""
         cfg = self.cfg
         dev, dt = images.device, images.dtype
@@ -483,7 +486,7 @@ class AIRModel(nn.Module):
                     head.prepare()
             if self.vae_rec_mean.fuse and self.vae_rec_mean.defer and images.is_cuda and images.dtype == torch.float32:
                 self._vae_pair.prepare()
-        if cfg.always_max_steps and cfg.batched_tail and cfg.stacked_kl:
+        if train and cfg.always_max_steps and cfg.batched_tail and cfg.stacked_kl:
             return self._forward_batched_tail(images, noise, global_batch, recon_loss_fn)
         stop_sum = z(B)
         inf_state, gen_state = (z(B, H), z(B, H)), (z(B, H), z(B, H))
@@ -525,8 +528,16 @@ class AIRModel(nn.Module):
             else:
                 prior_lo = self.z_prior(self.z_prior_h(gen_prev_out, "relu")).reshape(B)                     # :609-615
             post_lo = self.z_post(self.z_post_h(out, "relu")).reshape(B)                                     # :620-623
-            y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
-                                                                          temp, thr)     # concrete.py:20-27, :631, :698-712
+            if train:
+                y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo, noise("concrete", step, (B,)), stop_sum,
+                                                                              temp, thr)     # concrete.py:20-27, :631, :698-712
+            else:
+                u = noise("concrete", step, (B,))
+                y_pre = (post_lo + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temp               # concrete.py:20-27
+                z_pres = torch.round(torch.sigmoid(y_pre))                                                    # :631, :634-635
+                active_prev = stop_sum < thr
+                stop_sum = stop_sum + (1.0 - z_pres)                                                          # :712
+                active = stop_sum < thr
             act_list.append(active)
             canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
 

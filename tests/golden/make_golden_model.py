@@ -77,7 +77,17 @@ for name, (cs, counts, gn, gm, gne, gb, gs, ga, minmax, zt) in CONFIGS.items():
     for k, v in tf.VARIABLES.items():
         out["w:" + k] = v.detach().numpy()
         out["g:" + k] = v.grad.numpy() if v.grad is not None else np.zeros(tuple(v.shape))
+    # the reference's TEST model (train=False, :634-635: z_pres rounded) on the same weights and noise
+    for v in tf.VARIABLES.values():
+        v.grad = None
+    tf._LAYER_COUNTS.clear(); tf._SCOPE.clear()
+    self.train, self.log_variables = False, {}
+    with torch.no_grad(), tf.variable_scope("air"):
+        ref.AIRModel._create_model(self)
+    out.update(test_steps=tf.STEP["t"], test_rec_num_digits=self.rec_num_digits.numpy(), test_rec_scales=self.rec_scales.numpy(),
+               test_rec_shifts=self.rec_shifts.numpy(), test_z_pres_probs=self.z_pres_probs.numpy(), test_reconstruction=self.reconstruction.numpy())
     np.savez_compressed(os.path.join(HERE, f"graph_model_{name}.npz"), **out)
-    print(name, "loss", out["loss"], "steps", out["steps"], "digits", out["rec_num_digits"], "variables", len(tf.VARIABLES))
+    print(name, "loss", out["loss"], "steps", out["steps"], "digits", out["rec_num_digits"], "variables", len(tf.VARIABLES),
+          "| test model: steps", out["test_steps"], "digits", out["test_rec_num_digits"])
     for k, v in tf.VARIABLES.items():
         print("   ", k, tuple(v.shape), "grad" if v.grad is not None else "NO GRAD")

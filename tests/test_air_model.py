@@ -421,3 +421,57 @@ def test_gradient_cleaning_and_clipping_equal_the_reference_lines():
         np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-12)
         assert np.all(tr.grads[slot].reshape(-1)[want.size:].numpy() == 0)
     assert torch.isfinite(tr.flat_grad).all()
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "all"])
+def test_rehosted_test_model_equals_the_reference_graph_run_on_the_tf_shim(name):
+    """``train=False`` (the reference's test model, z_pres rounded right after the sigmoid, :634-635) against the same
+    reference graph executed with ``self.train = False``: trip count, hard counts, scales, shifts, probabilities, canvas --
+    the quantities ``detection.evaluation`` consumes."""
+    g, cfg, model, params, mp = _load_reference_graph_run(name)
+    noise = lambda kind, step, shape: torch.tensor(g["noise_" + kind][step]).reshape(shape)
+    with torch.no_grad():
+        out = model(torch.tensor(g["images"]), noise=noise, train=False)
+    assert out["steps"] == int(g["test_steps"])
+    assert np.array_equal(out["rec_num_digits"].numpy(), g["test_rec_num_digits"])
+    np.testing.assert_allclose(out["rec_scales"].numpy(), g["test_rec_scales"], atol=1e-8)
+    np.testing.assert_allclose(out["rec_shifts"].numpy(), g["test_rec_shifts"], atol=1e-8)
+    np.testing.assert_allclose(out["z_pres_probs"].numpy(), g["test_z_pres_probs"], atol=1e-8)
+    np.testing.assert_allclose(out["reconstruction"].numpy(), g["test_reconstruction"], atol=2e-6)
+
+
+@pytest.mark.gpu
+def test_device_side_evaluation_pass_matches_the_reference_metrics(cuda_device):
+    """train_air_pr.py:314-334 on the device: test model (rounded z_pres) on a labelled batch from the on-device feeder,
+    detection metrics by the CUDA kernel -- against the oracle restatement of the reference's ``evaluation`` (itself pinned
+    to the reference function) fed with the same inferred boxes."""
+    from mog_asr_b200.air import evaluate_detection
+    from mog_asr_b200.dataset import DeviceMultiObjectDataset, default_sprites
+    from oracle import detection_ref
+    cfg = config_from_flags("mnist", "13")
+    torch.manual_seed(0)
+    model = AIRModel(cfg, ops=CudaOps()).to(cuda_device)
+    ds = DeviceMultiObjectDataset(default_sprites(32, 28, seed=2), 50, (1, 2, 3), (11, 15), mode="disjoint", seed=4, device=cuda_device)
+    batch = ds.batch(0, 96)
+    gen = torch.Generator(device=cuda_device).manual_seed(9)
+    bank = {}
+
+    def noise(kind, step, shape):                       # the same draws for both passes
+        key = (kind, step)
+        if key not in bank:
+            bank[key] = (torch.rand(shape, device=cuda_device, generator=gen).clamp(1e-4, 1 - 1e-4) if kind == "concrete"
+                         else torch.randn(shape, device=cuda_device, generator=gen))
+        return bank[key]
+    res = evaluate_detection(model, batch, noise=noise)
+    with torch.no_grad():
+        out = model(torch.clamp(batch["images"], 0, 1), noise=noise, train=False)
+    pos, size, num = (batch[k].cpu().numpy() for k in ("pos", "size", "num"))
+    gt_pos = [pos[b, :num[b]].reshape(-1).tolist() for b in range(len(num))]
+    gt_size = [size[b, :num[b]].reshape(-1).tolist() for b in range(len(num))]
+    want = detection_ref.evaluation(gt_pos, gt_size, out["rec_shifts"].cpu().numpy(), out["rec_scales"].cpu().numpy(),
+                                    out["rec_num_digits"].cpu().numpy(), csize=50)
+    np.testing.assert_allclose(res["precision"].cpu().numpy(), want[0], atol=1e-12)
+    np.testing.assert_allclose(res["recall"].cpu().numpy(), want[1], atol=1e-12)
+    for k, w in zip(("gt_max_iou", "detected_max_iou", "global_iou"), want[2:]):
+        np.testing.assert_allclose(float(res[k]), w, atol=1e-12)
+    assert 0.0 <= float(res["accuracy"]) <= 1.0 and 1 <= res["steps"] <= cfg.max_steps
