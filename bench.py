@@ -190,12 +190,14 @@ class ClockSampler(threading.Thread):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def footprint_counts(torch, M, theta, in_size, out_size):
-    """F[b] = distinct source pixels image b addresses.  For the axis-aligned thetas of this workload the
-    tap set is a cross product, so F = |{x0,x1 over columns}| * |{y0,y1 over rows}|."""
+    """(F[b], G[b]): F = distinct source pixels image b addresses, G = output pixels whose taps are inside the source on
+    both axes (the only part of the upstream gradient that reaches dU or dtheta: outside it the taps cancel).  For the
+    axis-aligned thetas of this workload both are cross products of per-axis counts."""
     Hs, Ws = in_size
     Ho, Wo = out_size
     B = theta.shape[0]
     F = torch.empty(B, dtype=torch.int64, device=theta.device)
+    G = torch.empty(B, dtype=torch.int64, device=theta.device)
     step = max(1, (1 << 27) // (Ho * Wo))
     for b0 in range(0, B, step):
         c = M.stn_corners(theta[b0:b0 + step], in_size, out_size).view(4, -1, Ho, Wo).long()
@@ -207,7 +209,8 @@ def footprint_counts(torch, M, theta, in_size, out_size):
         ys.scatter_(1, c[2, :, :, 0], True)
         ys.scatter_(1, c[3, :, :, 0], True)
         F[b0:b0 + nb] = xs.sum(1) * ys.sum(1)
-    return F
+        G[b0:b0 + nb] = (c[0, :, 0, :] != c[1, :, 0, :]).sum(1) * (c[2, :, :, 0] != c[3, :, :, 0]).sum(1)
+    return F, G
 
 
 class GpuWorkload:
@@ -238,6 +241,7 @@ class GpuWorkload:
         self.dth = torch.empty((B, 6), device=dev)
         self.stream = torch.cuda.current_stream(dev).cuda_stream
         self.kinds = ("read_fwd", "read_bwd", "write_fwd", "write_bwd")
+        self.nsteps = AIR_STEPS
 
     def launch(self, kind, t):
         a, L, ck = self.a, self.L, self.lib.check
@@ -246,6 +250,9 @@ class GpuWorkload:
             ck(L.mog_stn_forward(self.U.data_ptr(), self.th_r[t].data_ptr(), self.out_r.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), kind)
         elif kind == "read_bwd":
             ck(L.mog_stn_backward(self.U.data_ptr(), self.th_r[t].data_ptr(), self.g_r[t].data_ptr(), self.dU_r.data_ptr(),
+                                  self.dth.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), kind)
+        elif kind == "read_bwd_dtheta":   # the AIR read call site: the input batch needs no gradient (dU = NULL)
+            ck(L.mog_stn_backward(self.U.data_ptr(), self.th_r[t].data_ptr(), self.g_r[t].data_ptr(), None,
                                   self.dth.data_ptr(), B, cs, cs, 1, gs, gs, 1, st), kind)
         elif kind == "write_fwd":
             ck(L.mog_stn_forward(self.W[t].data_ptr(), self.th_w[t].data_ptr(), self.out_w.data_ptr(), B, gs, gs, 1, cs, cs, 1, st), kind)
@@ -267,18 +274,26 @@ class GpuWorkload:
                     self.launch(kind, t)
 
     def algorithmic_bytes(self):
-        """Mean algorithmic bytes per launch for each kernel kind."""
+        """Mean algorithmic bytes per launch for each kernel kind.  SURVEY 8(d) with one correction:
+        a backward is charged only the part G of the upstream gradient whose taps lie inside the source -- the rest
+        cancels exactly and no implementation needs to read it -- instead of the whole output O:
+        fwd 4(F+O)+24, bwd(dU+dtheta) 4(G+F+S)+48, bwd(dtheta only) 4(G+F)+48.  `survey` keeps the uncorrected figures."""
         torch, a = self.torch, self.a
         cs, gs = a.canvas, a.glimpse
-        out = {k: 0.0 for k in self.kinds}
-        for t in range(AIR_STEPS):
-            Fr = footprint_counts(torch, self.M, self.th_r[t], (cs, cs), (gs, gs)).double()
-            Fw = footprint_counts(torch, self.M, self.th_w[t], (gs, gs), (cs, cs)).double()
+        n = self.th_r.shape[0]
+        out = {k: 0.0 for k in ("read_fwd", "read_bwd", "read_bwd_dtheta", "write_fwd", "write_bwd")}
+        self.survey_bytes = {k: 0.0 for k in ("read_bwd", "write_bwd")}
+        for t in range(n):
+            Fr, Gr = (v.double() for v in footprint_counts(torch, self.M, self.th_r[t], (cs, cs), (gs, gs)))
+            Fw, Gw = (v.double() for v in footprint_counts(torch, self.M, self.th_w[t], (gs, gs), (cs, cs)))
             O_r, S_r, O_w, S_w = gs * gs, cs * cs, cs * cs, gs * gs
-            out["read_fwd"] += float((4 * (Fr + O_r) + 24).sum()) / AIR_STEPS
-            out["read_bwd"] += float((4 * (O_r + Fr + S_r) + 48).sum()) / AIR_STEPS
-            out["write_fwd"] += float((4 * (Fw + O_w) + 24).sum()) / AIR_STEPS
-            out["write_bwd"] += float((4 * (O_w + Fw + S_w) + 48).sum()) / AIR_STEPS
+            out["read_fwd"] += float((4 * (Fr + O_r) + 24).sum()) / n
+            out["read_bwd"] += float((4 * (Gr + Fr + S_r) + 48).sum()) / n
+            out["read_bwd_dtheta"] += float((4 * (Gr + Fr) + 48).sum()) / n
+            out["write_fwd"] += float((4 * (Fw + O_w) + 24).sum()) / n
+            out["write_bwd"] += float((4 * (Gw + Fw + S_w) + 48).sum()) / n
+            self.survey_bytes["read_bwd"] += float((4 * (O_r + Fr + S_r) + 48).sum()) / n
+            self.survey_bytes["write_bwd"] += float((4 * (O_w + Fw + S_w) + 48).sum()) / n
         return out
 
 
@@ -650,7 +665,7 @@ def run_ours(a):
                         algorithmic_bytes_per_launch=abytes[dom], peak_source=peak_src,
                         note="write_bwd can exceed 1.0: the algorithmic count charges the whole canvas gradient (4*O), "
                              "the kernel reads only the in-range rows/columns (the others cancel exactly)",
-                        step_alg_gbs=sum(abytes.values()) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9 * 1.0,
+                        step_alg_gbs=sum(abytes[k] for k in wl.kinds) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9,
                         kernels=kernels)
         roofline["step_frac"] = roofline["step_alg_gbs"] / peak
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
@@ -726,7 +741,7 @@ def run_sweep(a):
                 ab = wl.algorithmic_bytes()
                 row = dict(canvas=canvas, glimpse=glimpse, regime=regime, batch=c.batch, ms_per_step=ms,
                            glimpses_per_sec=c.batch * 2 * AIR_STEPS / (ms * 1e-3),
-                           step_alg_gbs=sum(ab.values()) * AIR_STEPS / (ms * 1e-3) / 1e9,
+                           step_alg_gbs=sum(ab[k] for k in wl.kinds) * AIR_STEPS / (ms * 1e-3) / 1e9,
                            kernels={k: dict(us=kern_ms[k] * 1e3, alg_mb=ab[k] / 1e6, gbs=ab[k] / (kern_ms[k] * 1e-3) / 1e9,
                                             frac=ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds})
                 row["step_frac"] = row["step_alg_gbs"] / peak

@@ -226,7 +226,8 @@ class _FusedHead(torch.autograd.Function):
     stashed ``(x, skip, dpre1)`` rows (``_MeanVar.flush_head``) -- the deferred-weight-gradient scheme of the loop."""
 
     @staticmethod
-    def forward(ctx, x, skip, eps, w1cat, head, act):
+    def forward(ctx, x, skip, eps, w1cat, head, act, _anchor):
+        # ``_anchor`` (a parameter of the head) only makes sure the node exists when no data input requires grad
         L = _lib.load()
         hm, m, hv, v = head.hm, head.m, head.hv, head.v
         B, K = x.shape
@@ -266,7 +267,8 @@ class _FusedHead(torch.autograd.Function):
                                                _p(m.weight.grad), _p(m.bias.grad), _p(v.weight.grad), _p(v.bias.grad), _stream(x)),
                        "mog_air_head_backward")
         head._head_stash.append((x, skip, dpre1))
-        return torch.mm(dpre1, w1cat), dskip, None, None, None, None
+        dx = torch.mm(dpre1, w1cat) if ctx.needs_input_grad[0] else None
+        return dx, dskip, None, None, None, None, None
 
 
 def fused_head(head, x, skip, eps, act=None):
@@ -274,7 +276,7 @@ def fused_head(head, x, skip, eps, act=None):
     _need_cuda(x, "x")
     a = _ACT[act]
     mean, logvar, latent, squashed = _FusedHead.apply(x.float().contiguous(), None if skip is None else skip.float().contiguous(),
-                                                      eps.float().contiguous(), head._w1cat, head, a)
+                                                      eps.float().contiguous(), head._w1cat, head, a, head.m.weight)
     return mean, logvar, latent, (squashed if a else None)
 
 
@@ -286,9 +288,12 @@ class _FusedLinearAct(torch.autograd.Function):
     The layer's weight / bias gradients go through its deferred stash (``(x, dpre)`` rows, one GEMM per training step)."""
 
     @staticmethod
-    def forward(ctx, x, layer, act):
+    def forward(ctx, x, w, bias, layer, act):
+        # ``w`` / ``bias`` are autograd inputs on purpose (their gradients are returned as None and travel through the
+        # layer's stash instead): with them the node exists even when ``x`` does not require grad -- the first loop
+        # iteration feeds an all-zero state to the z_pres prior head (air_number_bbox_location.py:609-615), and without a
+        # node that iteration's weight-gradient rows would be lost.
         L = _lib.load()
-        w, bias = layer.weight, layer.bias
         y = torch.mm(x, w.t())
         B, N = y.shape
         with torch.cuda.device(x.device):
@@ -311,19 +316,20 @@ class _FusedLinearAct(torch.autograd.Function):
         else:
             dpre = g
         layer._stash.append((x, dpre))
-        return torch.mm(dpre, layer.weight), None, None
+        dx = torch.mm(dpre, layer.weight) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None
 
 
 def linear_act(layer, x, act=None):
     _need_cuda(x, "x")
-    return _FusedLinearAct.apply(x.float().contiguous(), layer, _ACT_DENSE[act])
+    return _FusedLinearAct.apply(x.float().contiguous(), layer.weight, layer.bias, layer, _ACT_DENSE[act])
 
 
 class _FusedLinearGauss(torch.autograd.Function):
     """mean / log-variance layers sharing their input, plus the sample: one GEMM on ``[Wmean | Wlogvar]`` and one kernel."""
 
     @staticmethod
-    def forward(ctx, x, eps, pair):
+    def forward(ctx, x, eps, pair, _anchor):
         L = _lib.load()
         pre = torch.mm(x, pair.wcat.t())                                  # [B, 2L]
         B, Ld = x.shape[0], pair.mean_layer.weight.shape[0]
@@ -349,9 +355,10 @@ class _FusedLinearGauss(torch.autograd.Function):
             _lib.check(L.mog_air_bias_gauss_backward(_p(logvar), _p(eps), _p(c(g_mean)), _p(c(g_logvar)), _p(c(g_latent)), _p(dpre), B, Ld,
                                                      _stream(x)), "mog_air_bias_gauss_backward")
         ctx.pair.stash.append((x, dpre))
-        return torch.mm(dpre, wcat), None, None
+        dx = torch.mm(dpre, wcat) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None
 
 
 def linear_gauss(pair, x, eps):
     _need_cuda(x, "x")
-    return _FusedLinearGauss.apply(x.float().contiguous(), eps.float().contiguous(), pair)
+    return _FusedLinearGauss.apply(x.float().contiguous(), eps.float().contiguous(), pair, pair.mean_layer.weight)

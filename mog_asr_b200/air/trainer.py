@@ -24,6 +24,8 @@ class Trainer:
                  ops=None, dtype=torch.float32, defer_weight_grads=True):
         self.cfg, self.device, self.pg = cfg, torch.device(device), process_group
         self.world = dist.get_world_size(process_group) if process_group is not None else 1
+        self.rank = dist.get_rank(process_group) if process_group is not None else 0
+        self.seed = seed
         self.global_batch = global_batch
         torch.manual_seed(seed)                       # identical initial parameters on every rank
         if ops is None:
@@ -125,6 +127,14 @@ class Trainer:
         cs2 = self.cfg.canvas_size ** 2
         self.static_images = torch.zeros((batch_size, cs2), device=self.device)
         noise = lambda kind, step, shape: self._noise(kind, step, shape, generator="default")   # graph-safe default generator
+        # The warm-up runs real steps (allocator, cuBLAS handles, NCCL): snapshot the training state first and put it
+        # back afterwards, so that capturing changes neither the parameters nor Adam's moments / step count.
+        with torch.no_grad():
+            snap = [[t.clone() for t in ts] for ts in (self.params, self.m, self.v)]
+        t_host, t_dev = self.t, self.t_dev.clone()
+        # the captured graph draws from the default CUDA generator: give every rank its own stream of draws, like
+        # the eager path's per-rank generator (identical seeds would repeat the same noise on every batch shard)
+        torch.cuda.manual_seed(self.seed + 1 + self.rank)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
@@ -132,6 +142,13 @@ class Trainer:
                 self.step(self.static_images, noise=noise)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        with torch.no_grad():
+            for ts, saved in zip((self.params, self.m, self.v), snap):
+                for t, s0 in zip(ts, saved):
+                    t.copy_(s0)
+            self.t_dev.copy_(t_dev)
+        self.t = t_host
+        self.flat_grad.zero_()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = self.step(self.static_images, noise=noise)

@@ -9,10 +9,15 @@
 // are bit-exact for finite inputs too.  Gradients are fp32 with a different (tree) summation order.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mog_common.cuh"
 #include "mog_stn_warp.cuh"
+#include "mog_stn_bwd.cuh"
+#include "mog_stn_bwd_tma.cuh"
+
+#include <cudaTypedefs.h>
 
 namespace mog {
 
@@ -148,11 +153,106 @@ static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
     return MOG_OK;
 }
 
+template <bool COMPOSITE, int NJC>
+static int launch_bwd_group(const BwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)kWarpsPerCta * bwd2_warp_smem_words(a.g) * sizeof(int) + (a.coop_zero == 2 ? kZeroBytes : 0);
+    MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Ws=%d too large for the per-warp row table", a.g.Ho, a.g.Ws);
+    if (int rc = set_smem(stn_bwd_group_kernel<COMPOSITE, NJC>, smem)) return rc;
+    const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
+    stn_bwd_group_kernel<COMPOSITE, NJC><<<grid_for(ctas, MOG_BWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_group_kernel");
+    return MOG_OK;
+}
+
+// ---- tensor maps for the TMA-staged backward --------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up through the runtime so that the library links against
+// cudart only.  Encoding is host arithmetic (no driver state), done per call: the library stays stateless.
+static PFN_cuTensorMapEncodeTiled_v12000 tmap_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+    }();
+    return fn;
+}
+
+// fp32 tensor [n][h][w] (dense), box [1][box_h][box_w]; out-of-bounds elements arrive as zeros
+static bool make_tmap3(CUtensorMap* m, const void* base, int w, int h, long long n, int box_w, int box_h) {
+    PFN_cuTensorMapEncodeTiled_v12000 enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// Write direction (small source, wide output): source staged whole, gradient tiles through an mbarrier ring.
+static bool bwd_tma_eligible(const BwdArgs& a) {
+    static const int on = env_flag("MOG_BWD_TMA", 1);
+    const Geo& g = a.g;
+    return on && g.C == 1 && a.u_div == 1 && g.S <= kTmaMaxSrc && g.Ws % 4 == 0 && g.Ws <= 256 && g.Hs <= 256 && g.Wo % 4 == 0 &&
+           g.Wo >= kTmaSW && g.Ho >= kTmaTR && a.Bsrc < (1ll << 31) && (reinterpret_cast<uintptr_t>(a.U) & 15) == 0 &&
+           (reinterpret_cast<uintptr_t>(a.gout) & 15) == 0;
+}
+
+template <bool COMPOSITE>
+static int launch_bwd_tma(const BwdArgs& a, cudaStream_t st, bool* launched) {
+    *launched = false;
+    CUtensorMap tmU, tmG;
+    if (!make_tmap3(&tmU, a.U, a.g.Ws, a.g.Hs, a.Bsrc, a.g.Ws, a.g.Hs) || !make_tmap3(&tmG, a.gout, a.g.Wo, a.g.Ho, a.Bsrc, kTmaSW, kTmaTR))
+        return MOG_OK;   // no encoder / rejected shape: the caller falls back to the register-load kernel
+    const size_t smem = (size_t)kWarpsPerCta * bwd_tma_warp_smem_bytes(a.g);
+    if (smem > (size_t)kMaxSmemBytes) return MOG_OK;
+    if (int rc = set_smem(stn_bwd_tma_kernel<COMPOSITE>, smem)) return rc;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_bwd_tma_kernel<COMPOSITE>, kWarpThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
+    stn_bwd_tma_kernel<COMPOSITE><<<grid_for(ctas, per_sm), kWarpThreads, smem, st>>>(tmU, tmG, a);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_tma_kernel");
+    *launched = true;
+    return MOG_OK;
+}
+
+// MOG_BWD_IMPL selects the separable-theta backward: "stream" (row-streaming gather form), "group" (grouped gather form,
+// register loads), "tma" (grouped form, TMA-staged, where eligible; else "group").  Read once.
+enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2 };
+static BwdImpl bwd_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOG_BWD_IMPL");
+        v = kBwdStream;
+        if (e && strcmp(e, "group") == 0) v = kBwdGroup;
+        if (e && strcmp(e, "tma") == 0) v = kBwdTma;
+    }
+    return (BwdImpl)v;
+}
+
 template <bool COMPOSITE>
 static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
+    const BwdImpl impl = bwd_impl();
+    if (impl == kBwdTma && bwd_tma_eligible(a)) {
+        bool launched = false;
+        if (int rc = launch_bwd_tma<COMPOSITE>(a, st, &launched)) return rc;
+        if (launched) return MOG_OK;
+    }
+    if (impl != kBwdStream) {
+        // grouped gather form: strips of 32 (narrow outputs) or 64 output columns
+        if (a.g.Wo <= 32) return launch_bwd_group<COMPOSITE, 1>(a, st);
+        return launch_bwd_group<COMPOSITE, 2>(a, st);
+    }
     // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
     const int nxc = (a.g.Ws + 31) / 32;
     if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);

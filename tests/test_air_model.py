@@ -218,6 +218,37 @@ def test_cuda_step_matches_oracle_step(cuda_device, flags):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("always_max", [False, True])
+@pytest.mark.parametrize("dn", ["13", "2"])
+def test_loop_form_gradients_with_the_fused_kernels(cuda_device, always_max, dn):
+    """The reference's loop form (``while any(stop_sum < thr)``, :386-390) and the fixed-trip-count form, learned z_pres
+    prior (``-dn 13``) and fixed step count (``-dn 2``), with the product operators (fused kernels, deferred weight
+    gradients) against the oracle's operators in float64: every parameter gradient, including the layers whose input
+    does not require grad in the first iteration (the z_pres prior head sees the all-zero initial state, :609-615)."""
+    cfg = config_from_flags("mnist", dn, gm=100.0, gne=10.0, always_max_steps=always_max)
+    B = 12
+    images, _ = make_images(B, 50, seed=8)
+    images = images.to(cuda_device)
+    got = Trainer(cfg, cuda_device, seed=5)
+    ref = Trainer(cfg, cuda_device, ops=OracleOps(), seed=5, dtype=torch.float64)
+    ref.model.load_state_dict(got.model.state_dict())
+    mse = lambda x, r: ((x - r) ** 2).sum(1) * 50.0
+    o_ref = ref.forward_backward(images.double(), noise=SeededNoise(3, B, device=cuda_device, dtype=torch.float64), recon_loss_fn=mse)
+    o_got = got.forward_backward(images, noise=SeededNoise(3, B, device=cuda_device), recon_loss_fn=mse)
+    assert o_got["steps"] == o_ref["steps"]
+    np.testing.assert_allclose(float(o_got["loss"]), float(o_ref["loss"]), rtol=2e-5)
+    g_ref, g_got = ref.flat_grad.cpu(), got.flat_grad.cpu().double()
+    off = 0
+    for (name, p) in got.model.named_parameters():
+        n = p.numel()
+        a, b = g_ref[off:off + n], g_got[off:off + n]
+        off += n
+        assert torch.isfinite(b).all(), name
+        assert float(a.abs().max()) > 0 or float(b.abs().max()) == 0, name
+        assert float((a - b).abs().max()) <= 2e-3 * float(a.abs().max()) + 1e-12, name
+
+
+@pytest.mark.gpu
 def test_one_step_changes_parameters_like_the_oracle_step(cuda_device):
     """After one full step (clip + TF-style Adam) both implementations hold the same parameters."""
     cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0, always_max_steps=True)
