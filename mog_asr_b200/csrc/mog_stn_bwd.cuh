@@ -9,14 +9,15 @@
 //        sum sx      += (Ic-Ia)*A  + (Id-Ib)*Bv          sum sx*yt += (Ic-Ia)*A2 + (Id-Ib)*B2
 //        sum sy      += E*(A+Bv)                         sum sy*yt += E*(A2+B2),  E = ax*(Ib-Ia) + bx*(Id-Ic)
 //      (ay + by = 1 inside the range); the x_t-weighted sums are formed per lane at the end of the image;
-//   3. forms the gradient row of source row y as V = A (this group) + Bv (previous group) and reduces
-//      ax*V and bx*V over the column runs (run(x) = the consecutive output columns whose left tap is x)
-//      with warp shuffles; the first lane of every run adds the two sums to a per-warp shared-memory row
-//      indexed by source column, which the warp then writes out coalesced: each dU row is written once,
-//      no atomics, deterministic.
-// Column parameters are recomputed from theta where they are needed (a dozen flops) instead of being
-// tabulated; the per-warp shared memory is a 16-byte entry per in-range output row (in stream order) and
-// one source row of floats -- a few KB, so occupancy is bounded by registers, not by shared memory.
+//   3. forms the gradient row of source row y as V = A (this group) + Bv (previous group) and turns it into
+//      source columns: ax*V and bx*V are summed over the column runs (run(x) = the consecutive output
+//      columns whose left tap is x) with warp shuffles; the first lane of every run (its head) fetches the
+//      right-tap sum of the neighbouring run with one more shuffle and stores T[x] with a plain store into
+//      a shared-memory row indexed by source column -- no read-modify-write, no atomics; the rows are then
+//      written out coalesced, each dU row once.
+// Wide outputs are processed in strips of 64 output columns; the one or two source columns two adjacent
+// strips share are handed over through a small shared-memory edge array instead of being accumulated in
+// global memory.  Everything is deterministic.
 #pragma once
 #include "mog_stn_warp.cuh"
 
@@ -26,17 +27,22 @@ namespace mog {
 #define MOG_BWD2_RB 4
 #endif
 #ifndef MOG_BWD2_MINB
-#define MOG_BWD2_MINB 12
+#define MOG_BWD2_MINB 10
 #endif
 
-constexpr int kPend2 = 2 * MOG_BWD2_RB * 32;   // floats of gradient rows a batch can leave pending (2 per output row x strip width)
-// per-warp shared memory (4-byte words): row table 4*Ho ({y0 byte offset | last-of-group, ay, by, yt} per in-range row,
-// in stream order) | pending gradient rows by output column (kPend2) and their source-row offsets | one gradient
-// row by source column, Ws + 1 floats
-__host__ __device__ inline int bwd2_warp_smem_words(const Geo& g) { return (4 * g.Ho + kPend2 + 2 * MOG_BWD2_RB + g.Ws + 1 + 3) & ~3; }
+constexpr int kBwdSlots = 2 * MOG_BWD2_RB;     // gradient rows a batch of MOG_BWD2_RB output rows can finish (a row may also flush a carry row)
+constexpr int kBwdSW = 64;                     // strip width (two 32-lane chunks)
+
+// per-warp shared memory of the emission machinery in 4-byte words: pending rows by output column (kBwdSlots x 64) |
+// their source-row byte offsets (kBwdSlots) | rows by source column (kBwdSlots x (Ws + 1)) | two edge arrays (Hs x 2 each)
+__host__ __device__ inline int bwd_emit_smem_words(const Geo& g) { return kBwdSlots * kBwdSW + kBwdSlots + kBwdSlots * (g.Ws + 1) + 4 * g.Hs; }
+// grouped kernel with register loads: row table 4*Ho ({y0 << 1 | last-of-group, ay, by, yt} per in-range row, in
+// stream order) in front of the emission area
+__host__ __device__ inline int bwd2_warp_smem_words(const Geo& g) { return (4 * g.Ho + bwd_emit_smem_words(g) + 3) & ~3; }
 
 struct RowP {      // one output row of a separable theta
-    int yoff;      // byte offset of source row y0 (clipped)
+    int y;         // source row y0 (clipped)
+    int yoff;      // its byte offset
     bool in;       // y0 != y1: the row is inside the source range
     float ay, by, yt;
 };
@@ -44,11 +50,237 @@ __device__ __forceinline__ RowP row_params(const Theta& th, const Geo& g, int i,
     RowP r;
     r.yt = lin_at(i, g.step_h);
     const Axis Y = axis_tap(affine_row(th.t[3], th.t[4], th.t[5], 0.0f, r.yt), g.hsc, g.Hs);
+    r.y = Y.c0;
     r.yoff = Y.c0 * ws4;
     r.in = Y.c0 != Y.c1;
     r.ay = Y.a;
     r.by = Y.b;
     return r;
+}
+
+// ---- per-strip state ------------------------------------------------------------------------------------------
+struct EmitSmem {
+    float* v;      // [kBwdSlots][64] pending rows by output column
+    int* sloty;    // [kBwdSlots] source row of every pending row
+    float* x;      // [kBwdSlots][Ws + 1] rows by source column (kept all-zero between emissions)
+    float* edge;   // [2][Hs][2] partial sums of the source columns shared by two adjacent strips
+};
+__device__ __forceinline__ EmitSmem emit_smem(int* base, const Geo& g) {
+    EmitSmem e;
+    e.v = reinterpret_cast<float*>(base);
+    e.sloty = base + kBwdSlots * kBwdSW;
+    e.x = reinterpret_cast<float*>(e.sloty + kBwdSlots);
+    e.edge = e.x + kBwdSlots * (g.Ws + 1);
+    return e;
+}
+
+// seg[c] packs, per lane and chunk: bits 0-5 number of lanes after this one in the same run; bit 8 head of a run;
+// bits 9-13 lane of the head whose source column is x - 1 (bit 14: there is one); bit 15 no head has column x + 1
+// (this head stores its right-tap sum itself); bit 16 one of the first two heads of a chunk other than the first (their
+// columns may hold what the previous chunk stored -- the other part of a run split by the chunk boundary, or its right-tap
+// sum: they accumulate instead of storing; the rows are all-zero otherwise)
+template <int NJC>
+struct Strip {
+    int xo[NJC], seg[NJC];
+    float caz[NJC], cbz[NJC], cax[NJC], cbx[NJC];
+    bool val[NJC];
+    int rmax;                  // longest run inside a chunk
+    int xlo, nxs;              // source columns [xlo, xlo + 32 nxs) cover the strip's taps
+    int in_lo, in_n;           // columns shared with the previous strip (their partial sums arrive through the edge array)
+    int ov_lo, ov_n;           // columns shared with the next strip (handed over, not stored)
+    int parity;                // edge array written by this strip
+};
+
+// columns [jfirst, je) of the strip are valid; lanes outside shadow a valid column with g = 0
+template <int NJC, bool COMPOSITE>
+__device__ __forceinline__ void strip_setup(Strip<NJC>& s, const Theta& th, const Geo& g, int js, int jfirst, int je, int jlo, int jhi,
+                                            float z, int lane, bool need_dU, int strip_index) {
+    s.rmax = 1;
+#pragma unroll
+    for (int c = 0; c < NJC; ++c) {
+        const int j = js + 32 * c + lane;
+        s.val[c] = j >= jfirst && j < je;
+        const Axis X = col_axis(th, g, min(max(j, jfirst), je - 1));
+        s.xo[c] = X.c0 * 4;
+        s.cax[c] = X.a; s.cbx[c] = X.b;
+        s.caz[c] = COMPOSITE ? X.a * z : X.a;
+        s.cbz[c] = COMPOSITE ? X.b * z : X.b;
+        // run structure inside the chunk (masked lanes belong to no run)
+        const int xprev = __shfl_up_sync(0xffffffffu, s.xo[c], 1);
+        const int vprev = __shfl_up_sync(0xffffffffu, (int)s.val[c], 1);
+        const bool cont = lane > 0 && s.val[c] && vprev != 0 && xprev == s.xo[c];   // continues lane - 1's run
+        const bool head = s.val[c] && !cont;
+        const unsigned cmask = __ballot_sync(0xffffffffu, cont);
+        const unsigned hmask = __ballot_sync(0xffffffffu, head);
+        const unsigned above = lane == 31 ? 0u : (cmask >> (lane + 1));
+        const int follow = __ffs(~above) - 1;
+        // neighbouring heads in lane order
+        const unsigned below_h = hmask & ((1u << lane) - 1u);
+        const unsigned above_h = lane == 31 ? 0u : (hmask >> (lane + 1));
+        const int prev_h = below_h ? 31 - __clz(below_h) : -1;
+        const int next_h = above_h ? lane + __ffs(above_h) : -1;
+        const int xp = __shfl_sync(0xffffffffu, s.xo[c], prev_h < 0 ? lane : prev_h);
+        const int xn = __shfl_sync(0xffffffffu, s.xo[c], next_h < 0 ? lane : next_h);
+        int donor = -1;          // head whose source column is x - 1
+        bool taker = false;      // some head has column x + 1 and will fetch this head's right-tap sum
+        if (prev_h >= 0 && xp == s.xo[c] - 4) donor = prev_h;
+        if (next_h >= 0 && xn == s.xo[c] - 4) donor = next_h;
+        if (prev_h >= 0 && xp == s.xo[c] + 4) taker = true;
+        if (next_h >= 0 && xn == s.xo[c] + 4) taker = true;
+        int pk = follow;
+        if (head) {
+            pk |= 256;
+            if (donor >= 0) pk |= (donor << 9) | (1 << 14);
+            if (!taker) pk |= 1 << 15;
+            if (c > 0 && __popc(below_h) <= 1) pk |= 1 << 16;
+        }
+        s.seg[c] = pk;
+        s.rmax = max(s.rmax, follow + 1);
+    }
+    s.rmax = __reduce_max_sync(0xffffffffu, s.rmax);
+    s.xlo = 0; s.nxs = 0; s.in_lo = s.in_n = s.ov_lo = s.ov_n = 0;
+    s.parity = strip_index & 1;
+    if (need_dU) {
+        auto range = [&](int ja, int jb, int& lo, int& hi) {   // source columns touched by output columns [ja, jb]
+            const int xa = col_axis(th, g, ja).c0, xb = col_axis(th, g, jb).c0;
+            lo = min(xa, xb);
+            hi = max(xa, xb) + 1;
+        };
+        int lo, hi;
+        range(jfirst, je - 1, lo, hi);
+        s.xlo = lo;
+        s.nxs = (hi - lo + 32) >> 5;
+        if (jfirst > jlo) {   // previous strip: columns [max(js - 32 NJC, jlo), jfirst - 1]
+            int plo, phi;
+            range(max(js - 32 * NJC, jlo), jfirst - 1, plo, phi);
+            s.in_lo = max(lo, plo);
+            s.in_n = max(0, min(hi, phi) - s.in_lo + 1);
+        }
+        if (je <= jhi) {      // next strip: columns [je, min(je + 32 NJC - 1, jhi)]
+            int nlo, nhi;
+            range(je, min(je + 32 * NJC - 1, jhi), nlo, nhi);
+            s.ov_lo = max(lo, nlo);
+            s.ov_n = max(0, min(hi, nhi) - s.ov_lo + 1);
+        }
+    }
+}
+
+// Turn the pending rows (slots [0, nslots) of e.v, by output column) into dU rows.
+template <int NJC>
+__device__ __forceinline__ void emit_slots(const Strip<NJC>& s, const EmitSmem& e, const Geo& g, char* dUbc, int nslots, int lane,
+                                           bool first_write) {
+    const int XP = g.Ws + 1;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < NJC; ++c) {
+        const int pk = s.seg[c];
+        const int follow = pk & 63;
+        const bool head = (pk & 256) != 0;
+        const int donor = (pk >> 9) & 31;
+        const int xi = s.xo[c] >> 2;
+#pragma unroll 2
+        for (int k = 0; k < nslots; ++k) {
+            const float v = e.v[k * kBwdSW + 32 * c + lane];
+            const float va0 = s.caz[c] * v, vb0 = s.cbz[c] * v;
+            float va = va0, vb = vb0;
+#pragma unroll 1
+            for (int d = 1; d < s.rmax; ++d) {   // run sums (the lanes' own values travel, not their partial sums)
+                const float ua = __shfl_down_sync(0xffffffffu, va0, d), ub = __shfl_down_sync(0xffffffffu, vb0, d);
+                if (d <= follow) { va += ua; vb += ub; }
+            }
+            const float sbd = __shfl_sync(0xffffffffu, vb, (pk & (1 << 14)) ? donor : lane);
+            if (head) {
+                float* px = e.x + k * XP + xi;
+                const float T = (pk & (1 << 14)) ? va + sbd : va;
+                if (pk & (1 << 16)) {          // first head of a later chunk: the previous chunk may have stored here
+                    px[0] += T;
+                    if (pk & (1 << 15)) px[1] += vb;
+                } else {
+                    px[0] = T;
+                    if (pk & (1 << 15)) px[1] = vb;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    float* edge_out = e.edge + s.parity * 2 * g.Hs;
+    const float* edge_in = e.edge + (s.parity ^ 1) * 2 * g.Hs;
+#pragma unroll 1
+    for (int cx = 0; cx < s.nxs; ++cx) {
+        const int x = s.xlo + 32 * cx + lane;
+        if (x < g.Ws) {
+            const bool incoming = x >= s.in_lo && x < s.in_lo + s.in_n;
+            const bool outgoing = x >= s.ov_lo && x < s.ov_lo + s.ov_n;
+#pragma unroll 2
+            for (int k = 0; k < nslots; ++k) {
+                const int yrow = e.sloty[k];
+                float T = e.x[k * XP + x];
+                e.x[k * XP + x] = 0.f;
+                if (incoming) T += edge_in[2 * yrow + (x - s.in_lo)];
+                if (outgoing) edge_out[2 * yrow + (x - s.ov_lo)] = T;
+                else emit_px(dUbc + (yrow * g.Ws + x) * 4, T, true, first_write);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// One batch of RB output rows whose g values (gq) and taps (I, for rows that end a group) are in registers:
+// accumulate, finish groups (dtheta sums, pending dU rows).  Returns the number of pending rows.
+template <int NJC, int RB, bool COMPOSITE>
+__device__ __forceinline__ int batch_arith(const Strip<NJC>& s, const EmitSmem& e, const int4* rows, int nb, const int (&ey)[RB],
+                                           const float (&gq)[NJC][RB], const float (&I)[NJC][RB][4], float (&A)[NJC], float (&Bv)[NJC],
+                                           float (&A2)[NJC], float (&B2)[NJC], float (&car)[NJC], float (&SX)[NJC], float (&SXY)[NJC],
+                                           float (&SY)[NJC], float (&SYY)[NJC], float (&SZ)[NJC], int& ycar, bool need_taps,
+                                           bool need_dU, int lane) {
+    int nslots = 0;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        if (r < nb) {
+            const int4 er = rows[r];
+            const float ay = __int_as_float(er.y), by = __int_as_float(er.z);
+            const float ayt = ay * __int_as_float(er.w), byt = by * __int_as_float(er.w);
+#pragma unroll
+            for (int c = 0; c < NJC; ++c) {
+                const float gv = s.val[c] ? gq[c][r] : 0.f;
+                A[c] = fmaf(ay, gv, A[c]);   Bv[c] = fmaf(by, gv, Bv[c]);
+                A2[c] = fmaf(ayt, gv, A2[c]); B2[c] = fmaf(byt, gv, B2[c]);
+            }
+            if (ey[r] & 1) {
+                const int yrow = ey[r] >> 1;
+                if (need_taps) {
+#pragma unroll
+                    for (int c = 0; c < NJC; ++c) {
+                        const float Ia = I[c][r][0], Ib = I[c][r][1], Ic = I[c][r][2], Id = I[c][r][3];
+                        const float dxa = Ic - Ia, dxb = Id - Ib;
+                        SX[c] = fmaf(dxa, A[c], fmaf(dxb, Bv[c], SX[c]));
+                        SXY[c] = fmaf(dxa, A2[c], fmaf(dxb, B2[c], SXY[c]));
+                        const float E = fmaf(s.cax[c], Ib - Ia, s.cbx[c] * (Id - Ic));
+                        SY[c] = fmaf(E, A[c] + Bv[c], SY[c]);
+                        SYY[c] = fmaf(E, A2[c] + B2[c], SYY[c]);
+                        if (COMPOSITE)   // dz = sum g * sample  (:722-727)
+                            SZ[c] = fmaf(fmaf(s.cax[c], Ia, s.cbx[c] * Ic), A[c], fmaf(fmaf(s.cax[c], Ib, s.cbx[c] * Id), Bv[c], SZ[c]));
+                    }
+                }
+                if (need_dU) {
+                    if (ycar >= 0 && ycar != yrow) {   // the previous group's lower row stands alone
+                        if (lane == 0) e.sloty[nslots] = ycar;
+#pragma unroll
+                        for (int c = 0; c < NJC; ++c) { e.v[nslots * kBwdSW + 32 * c + lane] = car[c]; car[c] = 0.f; }
+                        ++nslots;
+                    }
+                    if (lane == 0) e.sloty[nslots] = yrow;
+#pragma unroll
+                    for (int c = 0; c < NJC; ++c) { e.v[nslots * kBwdSW + 32 * c + lane] = A[c] + car[c]; car[c] = Bv[c]; }
+                    ++nslots;
+                    ycar = yrow + 1;
+                }
+#pragma unroll
+                for (int c = 0; c < NJC; ++c) A[c] = Bv[c] = A2[c] = B2[c] = 0.f;
+            }
+        }
+    }
+    return nslots;
 }
 
 template <bool COMPOSITE, int NJC>
@@ -61,10 +293,8 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD2_MINB) stn_bwd_group_ker
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int* s_base = reinterpret_cast<int*>(s_dyn) + warp * bwd2_warp_smem_words(g);
     int4* s_row = reinterpret_cast<int4*>(s_base);
-    float* s_v = reinterpret_cast<float*>(s_base + 4 * g.Ho);   // pending gradient rows (by output column), kSlots x SW
-    int* s_sloty = reinterpret_cast<int*>(s_v + kPend2);         // their source-row byte offsets
-    float* s_x = reinterpret_cast<float*>(s_sloty + 2 * MOG_BWD2_RB);   // gradient row under construction, by source column
-    for (int x = lane; x <= g.Ws; x += 32) s_x[x] = 0.f;
+    const EmitSmem em = emit_smem(s_base + 4 * g.Ho, g);
+    for (int k = lane; k < kBwdSlots * (g.Ws + 1); k += 32) em.x[k] = 0.f;
     __syncwarp();
     const long long nwarps = (long long)gridDim.x * kWarpsPerCta;
     const int SC = g.S * C;
@@ -156,8 +386,8 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD2_MINB) stn_bwd_group_ker
                     for (int ii = lane; ii < nrows; ii += 32) {
                         const RowP r = row_params(th, g, ascending ? ilo + ii : ihi - ii, ws4);
                         bool last = ii + 1 == nrows;
-                        if (!last) last = row_params(th, g, ascending ? ilo + ii + 1 : ihi - ii - 1, ws4).yoff != r.yoff;
-                        s_row[ii] = make_int4(r.yoff | (last ? 1 : 0), __float_as_int(r.ay), __float_as_int(r.by), __float_as_int(r.yt));
+                        if (!last) last = row_params(th, g, ascending ? ilo + ii + 1 : ihi - ii - 1, ws4).y != r.y;
+                        s_row[ii] = make_int4((r.y << 1) | (last ? 1 : 0), __float_as_int(r.ay), __float_as_int(r.by), __float_as_int(r.yt));
                     }
                     __syncwarp();
                     const char* Ubc = opaque(reinterpret_cast<const char*>(Ub));
@@ -166,58 +396,27 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD2_MINB) stn_bwd_group_ker
                     const float* gfirst = gb + (long long)(ascending ? ilo : ihi) * g.Wo;
 
                     // ---- strips of SW output columns; every strip streams the in-range rows once ----
-                    for (int js = jlo; js <= jhi; js += SW) {
+                    int strip_index = 0;
+                    for (int js = jlo; js <= jhi; js += SW, ++strip_index) {
                         const int je = min(js + SW, jhi + 1);   // strip = columns [js, je)
-                        const bool store_plain = first_write && js == jlo;   // later strips / transforms accumulate
-                        int xo[NJC], seg[NJC];   // byte offset of x0; (lanes after this one in the same run) | head-of-run << 8
-                        float caz[NJC], cbz[NJC], cax[NJC], cbx[NJC];
-                        bool val[NJC];
+                        Strip<NJC> sp;
+                        strip_setup<NJC, COMPOSITE>(sp, th, g, js, js, je, jlo, jhi, z, lane, need_dU, strip_index);
                         const float* gcol[NJC];
-                        int rmax = 1;   // longest run inside one 32-column chunk
 #pragma unroll
-                        for (int c = 0; c < NJC; ++c) {
-                            const int j = js + 32 * c + lane;
-                            val[c] = j < je;
-                            const int jc = val[c] ? j : je - 1;      // masked lanes shadow the strip's last column (their g is 0)
-                            const Axis X = col_axis(th, g, jc);
-                            xo[c] = X.c0 * 4;
-                            cax[c] = X.a; cbx[c] = X.b;
-                            caz[c] = COMPOSITE ? X.a * z : X.a;
-                            cbz[c] = COMPOSITE ? X.b * z : X.b;
-                            gcol[c] = gfirst + jc;
-                            // run structure inside the chunk (masked lanes belong to no run and never write)
-                            const int xprev = __shfl_up_sync(0xffffffffu, xo[c], 1);
-                            const int vprev = __shfl_up_sync(0xffffffffu, (int)val[c], 1);
-                            const bool cont = lane > 0 && val[c] && vprev != 0 && xprev == xo[c];   // continues lane - 1's run
-                            const unsigned eq_prev = __ballot_sync(0xffffffffu, cont);
-                            const unsigned above = lane == 31 ? 0u : (eq_prev >> (lane + 1));
-                            const int follow = __ffs(~above) - 1;   // lanes after this one in the same run
-                            seg[c] = follow | ((val[c] && !cont) ? 256 : 0);
-                            rmax = max(rmax, follow + 1);
-                        }
-                        rmax = __reduce_max_sync(0xffffffffu, rmax);
-                        int xlo = 0, nxs = 0;
-                        if (need_dU) {
-                            const int xa = col_axis(th, g, js).c0, xb = col_axis(th, g, je - 1).c0;
-                            xlo = min(xa, xb);
-                            nxs = (max(xa, xb) + 1 - xlo + 32) >> 5;   // source columns [xlo, max + 1]
-                        }
+                        for (int c = 0; c < NJC; ++c) gcol[c] = gfirst + min(js + 32 * c + lane, je - 1);
                         float A[NJC], Bv[NJC], A2[NJC], B2[NJC], car[NJC], SX[NJC], SXY[NJC], SY[NJC], SYY[NJC], SZ[NJC];
 #pragma unroll
                         for (int c = 0; c < NJC; ++c)
                             A[c] = Bv[c] = A2[c] = B2[c] = car[c] = SX[c] = SXY[c] = SY[c] = SYY[c] = SZ[c] = 0.f;
-                        int ycar = -1;   // byte offset of the source row the carry belongs to (-1: none pending)
+                        int ycar = -1;   // source row the carry belongs to (-1: none pending)
 
-                        // A batch leaves its finished gradient rows (by output column) pending in s_v; they are then turned
-                        // into source rows one at a time: run sums by shuffles, the first lane of every run adds them to
-                        // s_x (left tap, then right tap), s_x is written out coalesced and cleared.
                         bool done = false;
                         for (int ii0 = 0; !done; ii0 += kRB2) {
                             int nslots = 0;
                             if (ii0 < nrows) {
                                 const int nb = min(kRB2, nrows - ii0);
                                 // ---- loads of the batch: g of every row, the four taps at the end of every group ----
-                                int ey[kRB2];   // y0 byte offset | last-of-group (tail rows shadow the last valid row, never 'last')
+                                int ey[kRB2];   // source row << 1 | last-of-group (tail rows shadow the last valid row, never 'last')
                                 float gq[NJC][kRB2], I[NJC][kRB2][4];
 #pragma unroll
                                 for (int r = 0; r < kRB2; ++r) {
@@ -228,108 +427,28 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD2_MINB) stn_bwd_group_ker
                                     for (int c = 0; c < NJC; ++c) {
                                         gq[c][r] = __ldg(gcol[c] + ii * gstep);
                                         if ((ey[r] & 1) && need_taps) {
-                                            const char* pa = Ubc + (unsigned)((ey[r] & ~3) + xo[c]);
+                                            const char* pa = Ubc + (unsigned)((ey[r] >> 1) * ws4 + sp.xo[c]);
                                             I[c][r][0] = ldg_f32(pa);        I[c][r][2] = ldg_f32(pa + 4);
                                             I[c][r][1] = ldg_f32(pa + ws4);  I[c][r][3] = ldg_f32(pa + ws4 + 4);
                                         }
                                     }
                                 }
-                                // ---- arithmetic ----
-#pragma unroll
-                                for (int r = 0; r < kRB2; ++r) {
-                                    if (r < nb) {
-                                        const int4 er = s_row[ii0 + r];
-                                        const float ay = __int_as_float(er.y), by = __int_as_float(er.z);
-                                        const float ayt = ay * __int_as_float(er.w), byt = by * __int_as_float(er.w);
-#pragma unroll
-                                        for (int c = 0; c < NJC; ++c) {
-                                            const float gv = val[c] ? gq[c][r] : 0.f;
-                                            A[c] = fmaf(ay, gv, A[c]);   Bv[c] = fmaf(by, gv, Bv[c]);
-                                            A2[c] = fmaf(ayt, gv, A2[c]); B2[c] = fmaf(byt, gv, B2[c]);
-                                        }
-                                        if (ey[r] & 1) {
-                                            const int yoff = ey[r] & ~3;
-                                            if (need_taps) {
-#pragma unroll
-                                                for (int c = 0; c < NJC; ++c) {
-                                                    const float Ia = I[c][r][0], Ib = I[c][r][1], Ic = I[c][r][2], Id = I[c][r][3];
-                                                    const float dxa = Ic - Ia, dxb = Id - Ib;
-                                                    SX[c] = fmaf(dxa, A[c], fmaf(dxb, Bv[c], SX[c]));
-                                                    SXY[c] = fmaf(dxa, A2[c], fmaf(dxb, B2[c], SXY[c]));
-                                                    const float E = fmaf(cax[c], Ib - Ia, cbx[c] * (Id - Ic));
-                                                    SY[c] = fmaf(E, A[c] + Bv[c], SY[c]);
-                                                    SYY[c] = fmaf(E, A2[c] + B2[c], SYY[c]);
-                                                    if (COMPOSITE)   // dz = sum g * sample  (:722-727)
-                                                        SZ[c] = fmaf(fmaf(cax[c], Ia, cbx[c] * Ic), A[c],
-                                                                     fmaf(fmaf(cax[c], Ib, cbx[c] * Id), Bv[c], SZ[c]));
-                                                }
-                                            }
-                                            if (need_dU) {
-                                                if (ycar >= 0 && ycar != yoff) {   // the previous group's lower row stands alone
-                                                    if (lane == 0) s_sloty[nslots] = ycar;
-#pragma unroll
-                                                    for (int c = 0; c < NJC; ++c) { s_v[nslots * SW + 32 * c + lane] = car[c]; car[c] = 0.f; }
-                                                    ++nslots;
-                                                }
-                                                if (lane == 0) s_sloty[nslots] = yoff;
-#pragma unroll
-                                                for (int c = 0; c < NJC; ++c) { s_v[nslots * SW + 32 * c + lane] = A[c] + car[c]; car[c] = Bv[c]; }
-                                                ++nslots;
-                                                ycar = yoff + ws4;
-                                            }
-#pragma unroll
-                                            for (int c = 0; c < NJC; ++c) A[c] = Bv[c] = A2[c] = B2[c] = 0.f;
-                                        }
-                                    }
-                                }
+                                nslots = batch_arith<NJC, kRB2, COMPOSITE>(sp, em, s_row + ii0, nb, ey, gq, I, A, Bv, A2, B2, car, SX, SXY, SY, SYY,
+                                                                           SZ, ycar, need_taps, need_dU, lane);
                             } else {
                                 done = true;
                                 if (need_dU && ycar >= 0) {   // lower row of the last group
-                                    if (lane == 0) s_sloty[0] = ycar;
+                                    if (lane == 0) em.sloty[0] = ycar;
 #pragma unroll
-                                    for (int c = 0; c < NJC; ++c) s_v[32 * c + lane] = car[c];
+                                    for (int c = 0; c < NJC; ++c) em.v[32 * c + lane] = car[c];
                                     nslots = 1;
                                 }
                             }
-                            if (nslots > 0) {
-                                __syncwarp();
-#pragma unroll 1
-                                for (int k = 0; k < nslots; ++k) {
-                                    const int yoff = s_sloty[k];
-#pragma unroll
-                                    for (int c = 0; c < NJC; ++c) {
-                                        const float v = s_v[k * SW + 32 * c + lane];
-                                        const float va0 = caz[c] * v, vb0 = cbz[c] * v;
-                                        float va = va0, vb = vb0;
-                                        const int follow = seg[c] & 255;
-#pragma unroll 1
-                                        for (int d = 1; d < rmax; ++d) {   // (the lanes' own values travel, not their partial sums)
-                                            const float ua = __shfl_down_sync(0xffffffffu, va0, d), ub = __shfl_down_sync(0xffffffffu, vb0, d);
-                                            if (d <= follow) { va += ua; vb += ub; }
-                                        }
-                                        // (a lane only ever adds lanes of its own run, so the head's sum is the run's)
-                                        const bool head = seg[c] >= 256;
-                                        float* px = reinterpret_cast<float*>(reinterpret_cast<char*>(s_x) + xo[c]);
-                                        if (head) px[0] += va;
-                                        __syncwarp();
-                                        if (head) px[1] += vb;
-                                        __syncwarp();
-                                    }
-#pragma unroll 1
-                                    for (int cx = 0; cx < nxs; ++cx) {
-                                        const int x = xlo + 32 * cx + lane;
-                                        if (x < g.Ws) {
-                                            emit_px(dUbc + yoff + x * 4, s_x[x], true, store_plain);
-                                            s_x[x] = 0.f;
-                                        }
-                                    }
-                                    __syncwarp();
-                                }
-                            }
+                            if (nslots > 0) emit_slots<NJC>(sp, em, g, dUbc, nslots, lane, first_write);
                         }
 #pragma unroll
                         for (int c = 0; c < NJC; ++c) {
-                            if (val[c]) {
+                            if (sp.val[c]) {
                                 const float xt = lin_at(js + 32 * c + lane, g.step_w);
                                 p[0] = fmaf(xt, SX[c], p[0]); p[1] += SXY[c]; p[2] += SX[c];
                                 p[3] = fmaf(xt, SY[c], p[3]); p[4] += SYY[c]; p[5] += SY[c];

@@ -25,7 +25,7 @@ namespace mog {
 constexpr int kTmaTR = 8;                   // rows of a g tile
 constexpr int kTmaSW = 64;                  // columns of a g tile (one strip: two 32-lane chunks)
 constexpr int kTmaStages = 4;
-constexpr int kTmaRB = 4;                   // rows per arithmetic sub-batch
+constexpr int kTmaRB = MOG_BWD2_RB;         // rows per arithmetic sub-batch
 constexpr int kTmaTileBytes = kTmaTR * kTmaSW * 4;
 constexpr int kTmaMaxSrc = 4096;            // source pixels staged whole (64 x 64)
 #ifndef MOG_BWD_TMA_MINB
@@ -33,10 +33,9 @@ constexpr int kTmaMaxSrc = 4096;            // source pixels staged whole (64 x 
 #endif
 
 __host__ __device__ inline int align128(int v) { return (v + 127) & ~127; }
-// per-warp shared memory in bytes: source image | tile ring | tile row table | pending rows | their source rows |
-// one gradient row by source column | mbarriers
+// per-warp shared memory in bytes: source image | tile ring | tile row table | mbarriers | emission area (mog_stn_bwd.cuh)
 __host__ __device__ inline int bwd_tma_warp_smem_bytes(const Geo& g) {
-    return align128(g.S * 4) + kTmaStages * kTmaTileBytes + 128 + 2 * kTmaRB * kTmaSW * 4 + 128 + align128((g.Ws + 1) * 4) + 128;
+    return align128(g.S * 4) + kTmaStages * kTmaTileBytes + 128 + 128 + align128(bwd_emit_smem_words(g) * 4);
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -72,19 +71,18 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_TMA_MINB)
 stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmG, const BwdArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     constexpr int NJC = 2, SW = kTmaSW, TR = kTmaTR, RB = kTmaRB;
+    static_assert(SW == kBwdSW && TR % RB == 0, "tile shape");
     const Geo& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* s_base = s_raw + (size_t)warp * bwd_tma_warp_smem_bytes(g);
     float* s_U = reinterpret_cast<float*>(s_base);
     float* s_ring = reinterpret_cast<float*>(s_base + align128(g.S * 4));
     int4* s_rt = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(s_ring) + kTmaStages * kTmaTileBytes);
-    float* s_v = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_rt) + 128);
-    int* s_sloty = reinterpret_cast<int*>(s_v + 2 * RB * SW);
-    float* s_x = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_sloty) + 128);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_x) + align128((g.Ws + 1) * 4));
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_rt) + 128);
     uint64_t* bar_U = s_bar + kTmaStages;
+    const EmitSmem em = emit_smem(reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(s_bar) + 128), g);
 
-    for (int x = lane; x <= g.Ws; x += 32) s_x[x] = 0.f;
+    for (int k = lane; k < kBwdSlots * (g.Ws + 1); k += 32) em.x[k] = 0.f;
     if (lane == 0) {
         for (int s = 0; s <= kTmaStages; ++s) mbar_init(s_bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,9 +146,9 @@ stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                 char* dUbc = reinterpret_cast<char*>(dUb);
 
                 const int jbase = jlo & ~3;   // tile columns start on a 16-byte boundary
-                for (int js = jbase; js <= jhi; js += SW) {
+                int strip_index = 0;
+                for (int js = jbase; js <= jhi; js += SW, ++strip_index) {
                     const int jfirst = max(js, jlo), je = min(js + SW, jhi + 1);   // valid columns of the strip: [jfirst, je)
-                    const bool store_plain = js == jbase;
                     // tile t of this strip: stream rows [t TR, t TR + TR) = box rows of the tensor at (js, ybox(t), b)
                     auto issue_tile = [&](int t) {
                         if (lane == 0) {
@@ -162,76 +160,13 @@ stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                     };
                     for (int t = 0; t < min(kTmaStages, ntile); ++t) issue_tile(t);
 
-                    int xo[NJC], seg[NJC];
-                    float caz[NJC], cbz[NJC], cax[NJC], cbx[NJC];
-                    bool val[NJC];
-                    int rmax = 1;
-#pragma unroll
-                    for (int c = 0; c < NJC; ++c) {
-                        const int j = js + 32 * c + lane;
-                        val[c] = j >= jfirst && j < je;
-                        const Axis X = col_axis(th, g, min(max(j, jfirst), je - 1));   // masked lanes shadow a valid column (their g is 0)
-                        xo[c] = X.c0 * 4;
-                        cax[c] = X.a; cbx[c] = X.b;
-                        caz[c] = COMPOSITE ? X.a * z : X.a;
-                        cbz[c] = COMPOSITE ? X.b * z : X.b;
-                        const int xprev = __shfl_up_sync(0xffffffffu, xo[c], 1);
-                        const int vprev = __shfl_up_sync(0xffffffffu, (int)val[c], 1);
-                        const bool cont = lane > 0 && val[c] && vprev != 0 && xprev == xo[c];
-                        const unsigned eq_prev = __ballot_sync(0xffffffffu, cont);
-                        const unsigned above = lane == 31 ? 0u : (eq_prev >> (lane + 1));
-                        const int follow = __ffs(~above) - 1;
-                        seg[c] = follow | ((val[c] && !cont) ? 256 : 0);
-                        rmax = max(rmax, follow + 1);
-                    }
-                    rmax = __reduce_max_sync(0xffffffffu, rmax);
-                    int xlo = 0, nxs = 0;
-                    if (need_dU) {
-                        const int xa = col_axis(th, g, jfirst).c0, xb = col_axis(th, g, je - 1).c0;
-                        xlo = min(xa, xb);
-                        nxs = (max(xa, xb) + 1 - xlo + 32) >> 5;
-                    }
+                    Strip<NJC> sp;
+                    strip_setup<NJC, COMPOSITE>(sp, th, g, js, jfirst, je, jlo, jhi, z, lane, need_dU, strip_index);
                     float A[NJC], Bv[NJC], A2[NJC], B2[NJC], car[NJC], SX[NJC], SXY[NJC], SY[NJC], SYY[NJC], SZ[NJC];
 #pragma unroll
                     for (int c = 0; c < NJC; ++c)
                         A[c] = Bv[c] = A2[c] = B2[c] = car[c] = SX[c] = SXY[c] = SY[c] = SYY[c] = SZ[c] = 0.f;
                     int ycar = -1;
-
-                    // pending gradient rows (by output column, in s_v) -> source rows: run sums by shuffles, heads add to s_x
-                    auto emit_pending = [&](int nslots) {
-                        __syncwarp();
-#pragma unroll 1
-                        for (int k = 0; k < nslots; ++k) {
-                            const int yoff = s_sloty[k];
-#pragma unroll
-                            for (int c = 0; c < NJC; ++c) {
-                                const float v = s_v[k * SW + 32 * c + lane];
-                                const float va0 = caz[c] * v, vb0 = cbz[c] * v;
-                                float va = va0, vb = vb0;
-                                const int follow = seg[c] & 255;
-#pragma unroll 1
-                                for (int d = 1; d < rmax; ++d) {
-                                    const float ua = __shfl_down_sync(0xffffffffu, va0, d), ub = __shfl_down_sync(0xffffffffu, vb0, d);
-                                    if (d <= follow) { va += ua; vb += ub; }
-                                }
-                                const bool head = seg[c] >= 256;
-                                float* px = reinterpret_cast<float*>(reinterpret_cast<char*>(s_x) + xo[c]);
-                                if (head) px[0] += va;
-                                __syncwarp();
-                                if (head) px[1] += vb;
-                                __syncwarp();
-                            }
-#pragma unroll 1
-                            for (int cx = 0; cx < nxs; ++cx) {
-                                const int x = xlo + 32 * cx + lane;
-                                if (x < g.Ws) {
-                                    emit_px(dUbc + yoff + x * 4, s_x[x], true, store_plain);
-                                    s_x[x] = 0.f;
-                                }
-                            }
-                            __syncwarp();
-                        }
-                    };
 
                     for (int t = 0; t < ntile; ++t) {
                         const int st = t % kTmaStages;
@@ -240,12 +175,12 @@ stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                             const int ii = t * TR + lane;
                             const bool have = lane <= TR && ii < nrows;
                             RowP r;
-                            r.yoff = -4; r.ay = r.by = r.yt = 0.f; r.in = false;
+                            r.y = -2; r.yoff = 0; r.ay = r.by = r.yt = 0.f; r.in = false;
                             if (have) r = row_params(th, g, ascending ? ilo + ii : ihi - ii, ws4);
-                            const int ynext = __shfl_down_sync(0xffffffffu, r.yoff, 1);
-                            const bool last = ii + 1 >= nrows || ynext != r.yoff;
+                            const int ynext = __shfl_down_sync(0xffffffffu, r.y, 1);
+                            const bool last = ii + 1 >= nrows || ynext != r.y;
                             if (have && lane < TR)
-                                s_rt[lane] = make_int4(r.yoff | (last ? 1 : 0), __float_as_int(r.ay), __float_as_int(r.by), __float_as_int(r.yt));
+                                s_rt[lane] = make_int4((r.y << 1) | (last ? 1 : 0), __float_as_int(r.ay), __float_as_int(r.by), __float_as_int(r.yt));
                         }
                         mbar_wait(s_bar + st, (phase >> st) & 1u);
                         phase ^= 1u << st;
@@ -272,7 +207,7 @@ stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                                 for (int c = 0; c < NJC; ++c) {
                                     gq[c][r] = trow[32 * c];
                                     if ((ey[r] & 1) && need_taps) {
-                                        const char* pa = Usc + ((ey[r] & ~3) + xo[c]);
+                                        const char* pa = Usc + ((ey[r] >> 1) * ws4 + sp.xo[c]);
                                         I[c][r][0] = *reinterpret_cast<const float*>(pa);
                                         I[c][r][2] = *reinterpret_cast<const float*>(pa + 4);
                                         I[c][r][1] = *reinterpret_cast<const float*>(pa + ws4);
@@ -280,68 +215,22 @@ stn_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constan
                                     }
                                 }
                             }
-                            int nslots = 0;
-#pragma unroll
-                            for (int r = 0; r < RB; ++r) {
-                                if (r < nb) {
-                                    const int4 er = s_rt[r0 + r];
-                                    const float ay = __int_as_float(er.y), by = __int_as_float(er.z);
-                                    const float ayt = ay * __int_as_float(er.w), byt = by * __int_as_float(er.w);
-#pragma unroll
-                                    for (int c = 0; c < NJC; ++c) {
-                                        const float gv = val[c] ? gq[c][r] : 0.f;
-                                        A[c] = fmaf(ay, gv, A[c]);   Bv[c] = fmaf(by, gv, Bv[c]);
-                                        A2[c] = fmaf(ayt, gv, A2[c]); B2[c] = fmaf(byt, gv, B2[c]);
-                                    }
-                                    if (ey[r] & 1) {
-                                        const int yoff = ey[r] & ~3;
-                                        if (need_taps) {
-#pragma unroll
-                                            for (int c = 0; c < NJC; ++c) {
-                                                const float Ia = I[c][r][0], Ib = I[c][r][1], Ic = I[c][r][2], Id = I[c][r][3];
-                                                const float dxa = Ic - Ia, dxb = Id - Ib;
-                                                SX[c] = fmaf(dxa, A[c], fmaf(dxb, Bv[c], SX[c]));
-                                                SXY[c] = fmaf(dxa, A2[c], fmaf(dxb, B2[c], SXY[c]));
-                                                const float E = fmaf(cax[c], Ib - Ia, cbx[c] * (Id - Ic));
-                                                SY[c] = fmaf(E, A[c] + Bv[c], SY[c]);
-                                                SYY[c] = fmaf(E, A2[c] + B2[c], SYY[c]);
-                                                if (COMPOSITE)
-                                                    SZ[c] = fmaf(fmaf(cax[c], Ia, cbx[c] * Ic), A[c],
-                                                                 fmaf(fmaf(cax[c], Ib, cbx[c] * Id), Bv[c], SZ[c]));
-                                            }
-                                        }
-                                        if (need_dU) {
-                                            if (ycar >= 0 && ycar != yoff) {
-                                                if (lane == 0) s_sloty[nslots] = ycar;
-#pragma unroll
-                                                for (int c = 0; c < NJC; ++c) { s_v[nslots * SW + 32 * c + lane] = car[c]; car[c] = 0.f; }
-                                                ++nslots;
-                                            }
-                                            if (lane == 0) s_sloty[nslots] = yoff;
-#pragma unroll
-                                            for (int c = 0; c < NJC; ++c) { s_v[nslots * SW + 32 * c + lane] = A[c] + car[c]; car[c] = Bv[c]; }
-                                            ++nslots;
-                                            ycar = yoff + ws4;
-                                        }
-#pragma unroll
-                                        for (int c = 0; c < NJC; ++c) A[c] = Bv[c] = A2[c] = B2[c] = 0.f;
-                                    }
-                                }
-                            }
-                            if (nslots > 0) emit_pending(nslots);
+                            const int nslots = batch_arith<NJC, RB, COMPOSITE>(sp, em, s_rt + r0, nb, ey, gq, I, A, Bv, A2, B2, car, SX, SXY, SY, SYY, SZ,
+                                                                               ycar, need_taps, need_dU, lane);
+                            if (nslots > 0) emit_slots<NJC>(sp, em, g, dUbc, nslots, lane, true);
                         }
                         __syncwarp();   // every lane is done with stage st and with the row table
                         if (t + kTmaStages < ntile) issue_tile(t + kTmaStages);
                     }
                     if (need_dU && ycar >= 0) {   // lower row of the last group
-                        if (lane == 0) s_sloty[0] = ycar;
+                        if (lane == 0) em.sloty[0] = ycar;
 #pragma unroll
-                        for (int c = 0; c < NJC; ++c) s_v[32 * c + lane] = car[c];
-                        emit_pending(1);
+                        for (int c = 0; c < NJC; ++c) em.v[32 * c + lane] = car[c];
+                        emit_slots<NJC>(sp, em, g, dUbc, 1, lane, true);
                     }
 #pragma unroll
                     for (int c = 0; c < NJC; ++c) {
-                        if (val[c]) {
+                        if (sp.val[c]) {
                             const float xt = lin_at(js + 32 * c + lane, g.step_w);
                             p[0] = fmaf(xt, SX[c], p[0]); p[1] += SXY[c]; p[2] += SX[c];
                             p[3] = fmaf(xt, SY[c], p[3]); p[4] += SYY[c]; p[5] += SY[c];
