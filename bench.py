@@ -64,6 +64,17 @@ def workload_name(a):
             f"(read+write, fwd+bwd dU+dtheta), batch {a.batch}/GPU, theta={a.regime}-like")
 
 
+def config_dict(a):
+    """`config` of the JSON line: identical for both arms (what differs between them lives in `cpu_baseline.sample`)."""
+    ws_mb = a.batch * (2 * a.canvas ** 2 + 2 * a.glimpse ** 2) * 4 / 1e6
+    return dict(workload=workload_name(a),
+                l2=f"inputs larger than L2 (per-call working set {ws_mb:.0f} MB vs 126 MB L2); no flush",
+                timing="GPU arm: CUDA events on the launch stream, max over ranks; CPU arm: wall clock around the same calls")
+
+
+CPU_THREADS_CAP = 16   # the CPU arm runs on min(16, usable host threads): the ratio should not move with the host's core count
+
+
 def peak_hbm():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -93,8 +104,12 @@ def cpu_workload(a, nsample):
 
 
 def host_threads():
-    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what we want)."""
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which is not what we want)."""
     return len(os.sched_getaffinity(0))
+
+
+def cpu_threads():
+    return min(CPU_THREADS_CAP, host_threads())
 
 
 def cpu_step(a, wl, nthreads=0):
@@ -107,10 +122,12 @@ def cpu_step(a, wl, nthreads=0):
         RC.backward(W, th_w[t], (a.canvas, a.canvas), g_w, nthreads=nthreads)
 
 
-def cpu_measure(a, steps, warmup, nsample):
-    from oracle import stn_ref_c as RC
+def cpu_measure(a, steps, warmup, nsample, one_thread_too=True):
+    """The oracle's C restatement of the reference sampler on `cpu_threads()` host threads (capped so that the figure does
+    not move with the host), on a bounded sample of the same workload; beside it the single-thread figure -- the
+    reference's own setting (train_air_pr.py:243-244: intra_op = inter_op = 1)."""
     wl = cpu_workload(a, nsample)
-    cores = host_threads()
+    cores = cpu_threads()
     for _ in range(warmup):
         cpu_step(a, wl, cores)
     t0 = time.perf_counter()
@@ -118,10 +135,20 @@ def cpu_measure(a, steps, warmup, nsample):
         cpu_step(a, wl, cores)
     dt = time.perf_counter() - t0
     val = nsample * 2 * AIR_STEPS * steps / dt
-    return dict(value=val, unit=UNIT, cores=cores, kind="port",
-                sample=f"{nsample} canvases x {AIR_STEPS} AIR steps x (read+write) fwd+bwd x {steps} steps, "
-                       f"oracle/stn_ref.c with OpenMP over images ({cores} threads; os.cpu_count()={os.cpu_count()}, "
-                       f"affinity={len(os.sched_getaffinity(0))})"), dt / steps * 1e3
+    out = dict(value=val, unit=UNIT, cores=cores, kind="port",
+               sample=f"{nsample} canvases x {AIR_STEPS} AIR steps x (read+write) fwd+bwd x {steps} steps, "
+                      f"oracle/stn_ref.c with OpenMP over images ({cores} threads = min({CPU_THREADS_CAP}, usable); "
+                      f"os.cpu_count()={os.cpu_count()}, affinity={host_threads()}); the reference is TF-1.12 Python, not "
+                      f"installable here -- its sampler restated in C")
+    if one_thread_too:
+        n1 = max(8, nsample // 8)
+        wl1 = cpu_workload(a, n1)
+        cpu_step(a, wl1, 1)
+        t0 = time.perf_counter()
+        cpu_step(a, wl1, 1)
+        out["value_1thread"] = n1 * 2 * AIR_STEPS / (time.perf_counter() - t0)
+        out["sample_1thread"] = f"{n1} canvases, 1 step, 1 thread (the reference trainer's own thread setting)"
+    return out, dt / steps * 1e3
 
 
 def run_reference(a):
@@ -131,8 +158,7 @@ def run_reference(a):
     cb, ms = cpu_measure(a, a.steps, a.warmup, a.cpu_sample)
     line = dict(impl="reference", metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps,
                 warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=workload_name(a), note="reference is TF-1.12 Python (not installable "
-                "here); its sampler restated in C (oracle/stn_ref.c), timed on the host cores on a bounded sample"),
+                data="synthetic", config=config_dict(a),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     emit(line)
@@ -298,13 +324,16 @@ class GpuWorkload:
 
 
 def e2e_measure(a, dev, steps, warmup):
-    """Same 16*B glimpses per step, host (pinned) arrays in and out through mog_stn_fwd_bwd_host."""
+    """Same 16*B glimpses per step, host (pinned) arrays in and out through the host entry points.  Read direction: ONE
+    mog_stn_batch_fwd_bwd_host call (the reference's batch_transformer form: the canvases cross the bus once for their 8
+    thetas, dU -- summed over the 8 steps, what autodiff of 8 reads of one canvas yields -- comes back once).  Write
+    direction: 8 mog_stn_fwd_bwd_host calls (every step has its own window, gradient and output canvas)."""
     import torch
     from mog_asr_b200 import synth
     from mog_asr_b200.host_api import HostSampler
-    B, cs, gs = a.e2e_batch, a.canvas, a.glimpse
+    B, cs, gs, T = a.e2e_batch, a.canvas, a.glimpse, AIR_STEPS
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
-    U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, gs, gs, 1), pin(B, cs, cs, 1)
+    U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, T, gs, gs, 1), pin(B, cs, cs, 1)
     gdev = torch.Generator(device=dev).manual_seed(10)   # fill the host arrays from device-generated data (fast)
     for t, normal in ((U_h, False), (W_h, False), (g_r, True), (g_w, True)):
         tmp = (torch.randn if normal else torch.rand)(tuple(t.shape), device=dev, generator=gdev)
@@ -312,18 +341,21 @@ def e2e_measure(a, dev, steps, warmup):
         del tmp
     gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
     th_r, th_w = [], []
-    for t in range(AIR_STEPS):
+    for t in range(T):
         s, x, y = gen(B, seed=100 + t)
-        th_r.append(torch.from_numpy(synth.theta_read(s, x, y)).pin_memory())
+        th_r.append(synth.theta_read(s, x, y))
         th_w.append(torch.from_numpy(synth.theta_write(s, x, y)).pin_memory())
-    out_r, dU_r, out_w, dU_w, dth = pin(B, gs, gs, 1), pin(B, cs, cs, 1), pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, 6)
-    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(256, min(512, B // 8)))
-    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=max(256, min(512, B // 8)))
+    th_r = torch.from_numpy(np.ascontiguousarray(np.stack(th_r, 1))).pin_memory()          # [B, T, 6]
+    out_r, dU_r, out_w, dU_w = pin(B * T, gs, gs, 1), pin(B, cs, cs, 1), pin(B, cs, cs, 1), pin(B, gs, gs, 1)
+    dth_r, dth_w = pin(B, T, 6), pin(B, 6)
+    chunk = max(256, min(512, B // 8))
+    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(32, chunk // T), transforms=T)
+    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=chunk)
 
     def step():
-        for t in range(AIR_STEPS):
-            rd.fwd_bwd(U_h, th_r[t], g_r, out=out_r, dU=dU_r, dtheta=dth)
-            wr.fwd_bwd(W_h, th_w[t], g_w, out=out_w, dU=dU_w, dtheta=dth)
+        rd.batch_fwd_bwd(U_h, th_r, g_r, out=out_r, dU=dU_r, dtheta=dth_r)
+        for t in range(T):
+            wr.fwd_bwd(W_h, th_w[t], g_w, out=out_w, dU=dU_w, dtheta=dth_w)
 
     for _ in range(warmup):
         step()
@@ -334,10 +366,10 @@ def e2e_measure(a, dev, steps, warmup):
     torch.cuda.synchronize(dev)
     dt = (time.perf_counter() - t0) / steps
     fl = 4
-    h2d = AIR_STEPS * fl * (U_h.numel() + g_r.numel() + W_h.numel() + g_w.numel() + 12 * B)
-    d2h = AIR_STEPS * fl * (out_r.numel() + dU_r.numel() + out_w.numel() + dU_w.numel() + 12 * B)
-    chunks = -(-B // rd.chunk)  # launches: 2 kernels per chunk per call
-    return dt, h2d, d2h, AIR_STEPS * 2 * 2 * chunks
+    h2d = fl * (U_h.numel() + g_r.numel() + th_r.numel() + T * (W_h.numel() + g_w.numel() + 6 * B))
+    d2h = fl * (out_r.numel() + dU_r.numel() + dth_r.numel() + T * (out_w.numel() + dU_w.numel() + 6 * B))
+    launches = 2 * (-(-B // rd.chunk)) + T * 2 * (-(-B // wr.chunk))   # forward + backward per chunk and call
+    return dt, h2d, d2h, launches
 
 
 def config1_section(dev, no_cpu):
@@ -638,7 +670,8 @@ def run_ours(a):
         dt = max_over_ranks(dt)
         e2e = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
                    d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3, steps=e_steps, batch_per_gpu=a.e2e_batch,
-                   api="mog_stn_fwd_bwd_host (pinned host arrays in/out, chunked over 3 streams)")
+                   api="read: mog_stn_batch_fwd_bwd_host (canvases uploaded once for the 8 thetas, dU summed over them, downloaded "
+                       "once); write: 8 x mog_stn_fwd_bwd_host; pinned host arrays in/out, chunked over 3 streams")
     tc2 = time.perf_counter()
     sampler.stop_flag = True
     clocks = sampler.summary(tc0, tc2 if e2e else tc1)
@@ -653,27 +686,48 @@ def run_ours(a):
         nxc = lambda w: 1 if w <= 32 else (2 if w <= 64 else 4)
         sym = dict(read_fwd="stn_fwd_warp_kernel<false>", write_fwd="stn_fwd_warp_kernel<false>",
                    read_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.canvas)}>", write_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.glimpse)}>")
-        traffic, traffic_src = None, None
-        try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this cell
+        # physical DRAM bytes per launch of ALL four kernels, from the ncu capture committed with this bench line
+        # (tools/traffic_capture.py: dram__bytes_read.sum + dram__bytes_write.sum, same cell, same batch)
+        traffic, traffic_src, tj = None, None, None
+        try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-            if tj["cell"] == dict(canvas=a.canvas, glimpse=a.glimpse, regime=a.regime, batch=a.batch):
-                traffic, traffic_src = tj["bytes_per_launch"][dom], tj["source"]
+            if tj["cell"] != dict(canvas=a.canvas, glimpse=a.glimpse, regime=a.regime, batch=a.batch):
+                tj = None
         except Exception:
-            pass
+            tj = None
+        if tj is not None:
+            traffic, traffic_src = tj["bytes_per_launch"][dom], tj["source"]
+            for k in wl.kinds:
+                kernels[k]["traffic_bytes_per_launch"] = tj["bytes_per_launch"][k]
+                kernels[k]["frac_physical"] = tj["bytes_per_launch"][k] / (kern_ms[k] * 1e-3) / 1e9 / peak
+        # the AIR read call site asks for dtheta only (air_number_bbox_location.py:534-542): reported beside the dU + dtheta form
+        evs = []
+        for t in range(AIR_STEPS):
+            e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0_.record(); wl.launch("read_bwd_dtheta", t); e1_.record()
+            evs.append((e0_, e1_))
+        torch.cuda.synchronize(dev)
+        ms_dt = float(np.mean([x.elapsed_time(y) for x, y in evs]))
+        kernels["read_bwd_dtheta_only"] = dict(ms=ms_dt, alg_bytes_per_launch=abytes["read_bwd_dtheta"],
+                                               achieved_gbs=abytes["read_bwd_dtheta"] / (ms_dt * 1e-3) / 1e9,
+                                               frac=abytes["read_bwd_dtheta"] / (ms_dt * 1e-3) / 1e9 / peak,
+                                               note="not part of the timed step: the AIR-faithful read backward (no dU)")
         roofline = dict(bound="hbm", kernel=f"{sym[dom]} ({dom})", achieved=kernels[dom]["achieved_gbs"], peak=peak,
                         unit="GB/s", frac=kernels[dom]["frac"], traffic=traffic, traffic_source=traffic_src,
                         algorithmic_bytes_per_launch=abytes[dom], peak_source=peak_src,
-                        note="write_bwd can exceed 1.0: the algorithmic count charges the whole canvas gradient (4*O), "
-                             "the kernel reads only the in-range rows/columns (the others cancel exactly)",
+                        note="algorithmic bytes: fwd 4(F+O)+24, bwd 4(G+F+S)+48 with G = the in-range part of the upstream gradient "
+                             "(SURVEY 8(d) charges all of O; survey_bytes_per_launch keeps that figure); frac_physical uses measured DRAM bytes",
+                        survey_bytes_per_launch=getattr(wl, "survey_bytes", None),
                         step_alg_gbs=sum(abytes[k] for k in wl.kinds) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9,
                         kernels=kernels)
         roofline["step_frac"] = roofline["step_alg_gbs"] / peak
+        if tj is not None:
+            roofline["step_physical_gbs"] = sum(tj["bytes_per_launch"][k] for k in wl.kinds) * AIR_STEPS / (ms_per_step * 1e-3) / 1e9
+            roofline["step_frac_physical"] = roofline["step_physical_gbs"] / peak
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                     data="synthetic",
-                    config=dict(workload=workload_name(a), l2="inputs larger than L2 (per-call working set "
-                                f"{(wl.U.numel() * 2 + wl.out_r.numel() * 2) * 4 / 1e6:.0f} MB vs 126 MB L2); no flush",
-                                timing="CUDA events on the launch stream, max over ranks"),
+                    config=config_dict(a),
                     roofline=roofline, clocks=clocks, gpu_launches=4 * AIR_STEPS * a.steps)
         if e2e:
             line["e2e"] = e2e

@@ -78,6 +78,16 @@ MOG_API int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, const f
 /* Scratch needed by mog_stn_fwd_bwd_host for a given chunk size and stream count (returns 0 on bad args). */
 MOG_API size_t mog_stn_host_workspace_bytes(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo, int nstreams);
 
+/* batch_transformer form of the same (air/transformer.py:178-195): U_h [B][Hs][Ws][C] holds B source images, every one
+ * of them sampled with T transforms: thetas_h [B][T][6], gout_h / out_h [B][T][Ho][Wo][C] (the reference's output order,
+ * index b*T + t), dtheta_h [B][T][6] (nullable), dU_h [B][Hs][Ws][C] (nullable) = the gradient summed over the T
+ * transforms.  A source image crosses the bus once for its T transforms, dU once (or never: the AIR read site asks for
+ * dtheta only).  gout_h may be NULL when no gradient is requested.  chunk counts source images. */
+MOG_API int mog_stn_batch_fwd_bwd_host(const float* U_h, const float* thetas_h, const float* gout_h, float* out_h, float* dU_h,
+                               float* dtheta_h, int64_t B, int T, int Hs, int Ws, int C, int Ho, int Wo, int64_t chunk,
+                               void* workspace_d, size_t workspace_bytes, void* const* streams, int nstreams);
+MOG_API size_t mog_stn_batch_host_workspace_bytes(int64_t chunk, int T, int Hs, int Ws, int C, int Ho, int Wo, int nstreams);
+
 /* canvas_out[b] = canvas_in[b] + (stop_sum[b] < threshold ? z_pres[b] * sample(U[b]; theta[b]) : 0)
  * U is the [B][Hw][Ww] window (C = 1), canvases are [B][Hc][Wc]; canvas_out may alias canvas_in (the
  * in-place form touches only pixels that change).  stop_sum NULL = every image active. */

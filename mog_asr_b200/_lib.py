@@ -37,6 +37,9 @@ SIGNATURES = {
     "mog_stn_fwd_bwd_host": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _i64, _vp, ctypes.c_size_t,
                              ctypes.POINTER(ctypes.c_void_p), _int],
     "mog_stn_host_workspace_bytes": [_i64, _int, _int, _int, _int, _int, _int],
+    "mog_stn_batch_fwd_bwd_host": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _i64, _vp, ctypes.c_size_t,
+                                   ctypes.POINTER(ctypes.c_void_p), _int],
+    "mog_stn_batch_host_workspace_bytes": [_i64, _int, _int, _int, _int, _int, _int, _int],
     "mog_stn_write_composite_forward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
     "mog_stn_write_composite_backward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
     "mog_bce_recon_forward": [_vp, _vp, _vp, _vp, _i64, _int, _vp],
@@ -83,7 +86,7 @@ def load() -> ctypes.CDLL:
             for name, argtypes in SIGNATURES.items():
                 fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
                 fn.argtypes = argtypes
-                fn.restype = ctypes.c_size_t if name == "mog_stn_host_workspace_bytes" else ctypes.c_int
+                fn.restype = ctypes.c_size_t if name.endswith("host_workspace_bytes") else ctypes.c_int
             v = L.mog_version()
             if v != ABI_VERSION:
                 raise RuntimeError(f"libmogstn ABI version {v} != expected {ABI_VERSION}")

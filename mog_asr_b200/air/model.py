@@ -635,6 +635,62 @@ class AIRModel(nn.Module):
         return self._epilogue(images, canvas, act_l, H_, None, post_lo.t().contiguous(), torch.stack(per["shift"], 1),
                               torch.stack(per["scale"], 1), T, global_batch, recon_loss_fn)
 
+    # ---- the generation graph --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, batch_size: int, noise: Optional[Callable] = None, device=None, dtype=None):
+        """Samples from the generative model: the reference's ``_create_generation`` (``air_number_bbox_location.py:1124-1361``),
+        the third model-math call site of the sampler (``:1249``), fetched by the trainer as ``generated_samples``
+        (``train_air_pr.py:241,:389``).  Per step: generative LSTM on the previous step's latents (``:1151-1156``) -> learned
+        shift prior, sampled (``:1157-1169``) -> the scale is drawn from the fixed prior but then REPLACED by the constant
+        ``mean(constrains_area_minmax) / canvas_size`` (``:1199-1205``; the drawn latent still feeds the next step, ``:1209-1211``)
+        -> a VAE prior sample decoded and binarised by a Bernoulli draw (``vae_generation(..., sample_from_mean=True)``,
+        ``air/vae.py:51-86``) -> written onto the canvas with ``theta_w`` and the rounded Concrete ``z_pres`` of the learned (or
+        fixed-count) prior (``:1225-1303``); the loop stops when every image has stopped (``:1131-1135``).
+        ``noise(kind, step, shape)``: N(0,1) for 'shift' / 'scale' / 'vae', U(0,1) for 'concrete' and 'bernoulli'.
+        Returns ``samples [B, cs, cs, 1]``, ``num`` (objects per image), ``thetas [B, steps, 2, 3]`` (the write transforms the
+        reference hands to its bounding-box overlay) and ``steps``."""
+        cfg = self.cfg
+        p0 = next(self.parameters())
+        dev, dt = device or p0.device, dtype or p0.dtype
+        B = int(batch_size)
+        cs, ws, thr, temp = cfg.canvas_size, cfg.windows_size, cfg.stopping_threshold, cfg.z_pres_temperature
+        H, L = cfg.rnn_units, cfg.vae_latent_dimensions
+        if noise is None:
+            noise = lambda kind, step, shape: (torch.rand(shape, device=dev, dtype=dt) if kind in ("concrete", "bernoulli")
+                                               else torch.randn(shape, device=dev, dtype=dt))
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=dt)
+        stop_sum, gen_state = z(B), (z(B, H), z(B, H))
+        gen_prev_out, prev_latent, prev_ss = z(B, H), z(B, L), z(B, 3)
+        canvas, digits, thetas = z(B, cs, cs), torch.zeros(B, dtype=torch.int32, device=dev), []
+        scale_value = float(sum(cfg.constrains_area_minmax)) / len(cfg.constrains_area_minmax) / cs        # :1203-1204
+        scale = torch.full((B, 1), scale_value, device=dev, dtype=dt)
+        step = 0
+        while step < cfg.max_steps and bool((stop_sum < thr).any()):                                      # :1131-1135
+            gen_out, gen_state = self.gen_cell(torch.cat([prev_latent, prev_ss], -1), gen_state)           # :1151-1156
+            g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                   # :1157-1166
+            shift_latent = g_sh_mean + noise("shift", step, (B, 2)) * torch.sqrt(torch.exp(g_sh_lv))       # :1168
+            shift = torch.tanh(shift_latent)                                                               # :1169
+            scale_latent = cfg.scale_prior_mean + noise("scale", step, (B, 1)) * math.sqrt(cfg.scale_prior_variance)   # :1196-1200
+            latent = cfg.vae_prior_mean + noise("vae", step, (B, L)) * math.sqrt(cfg.vae_prior_variance)   # vae.py:63-66
+            mean = self._decode(latent)                                                                    # vae.py:68-81 (likelihood_std = 0)
+            window = torch.relu(torch.sign(mean - noise("bernoulli", step, (B, ws * ws))))                 # vae.py:83-84
+            _, theta_w = self.ops.thetas(shift, scale)                                                     # :1225-1246
+            thetas.append(theta_w.reshape(B, 2, 3))
+            if cfg.fix_steps is not None:                                                                  # :1261-1265
+                prior_lo = torch.full((B,), 100.0 if step < cfg.fix_steps else -100.0, device=dev, dtype=dt)
+            else:
+                prior_lo = self.z_prior(self.z_prior_h(gen_prev_out, "relu")).reshape(B)                   # :1267-1272
+            u = noise("concrete", step, (B,))
+            y_pre = (prior_lo + torch.log(u + 10e-10) - torch.log(1.0 - u + 10e-10)) / temp                # concrete.py:20-27
+            z_pres = torch.round(torch.sigmoid(y_pre))                                                     # :1281-1285
+            stop_sum = stop_sum + (1.0 - z_pres)                                                           # :1291
+            digits = digits + (stop_sum < thr).to(torch.int32)                                             # :1294-1295
+            canvas = self.ops.write_composite(canvas, window.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)   # :1249-1257,:1297-1303
+            gen_prev_out, prev_latent, prev_ss = gen_out, latent, torch.cat([shift_latent, scale_latent], -1)
+            step += 1
+        return dict(samples=canvas.reshape(B, cs, cs, 1), num=digits, steps=step,
+                    thetas=torch.stack(thetas, 1) if thetas else z(B, 0, 2, 3))
+
     def _epilogue(self, images, canvas, act_list, H_, kl, log_odds, shifts, scales, T, global_batch, recon_loss_fn):
         """everything after the loop: object counts, KL terms (:690-787,:930-935), reconstruction loss (:945-968),
         ASR regularisers (:645-681,:970-1069) and the loss (:1078-1079)"""

@@ -353,22 +353,28 @@ struct HostChunkLayout {
     size_t U, theta, gout, out, dU, dtheta, total;
 };
 
-static HostChunkLayout host_chunk_layout(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo) {
+// chunk = source images per chunk; every source image carries T transforms (T outputs, T thetas, T upstream gradients)
+static HostChunkLayout host_chunk_layout(int64_t chunk, int T, int Hs, int Ws, int C, int Ho, int Wo) {
     HostChunkLayout l;
     size_t o = 0;
     l.U = o;      o += align256((size_t)chunk * Hs * Ws * C * sizeof(float));
-    l.theta = o;  o += align256((size_t)chunk * 6 * sizeof(float));
-    l.gout = o;   o += align256((size_t)chunk * Ho * Wo * C * sizeof(float));
-    l.out = o;    o += align256((size_t)chunk * Ho * Wo * C * sizeof(float));
+    l.theta = o;  o += align256((size_t)chunk * T * 6 * sizeof(float));
+    l.gout = o;   o += align256((size_t)chunk * T * Ho * Wo * C * sizeof(float));
+    l.out = o;    o += align256((size_t)chunk * T * Ho * Wo * C * sizeof(float));
     l.dU = o;     o += align256((size_t)chunk * Hs * Ws * C * sizeof(float));
-    l.dtheta = o; o += align256((size_t)chunk * 6 * sizeof(float));
+    l.dtheta = o; o += align256((size_t)chunk * T * 6 * sizeof(float));
     l.total = o;
     return l;
 }
 
 extern "C" size_t mog_stn_host_workspace_bytes(int64_t chunk, int Hs, int Ws, int C, int Ho, int Wo, int nstreams) {
     if (chunk <= 0 || Hs <= 0 || Ws <= 0 || C <= 0 || Ho <= 0 || Wo <= 0 || nstreams <= 0) return 0;
-    return host_chunk_layout(chunk, Hs, Ws, C, Ho, Wo).total * (size_t)nstreams;
+    return host_chunk_layout(chunk, 1, Hs, Ws, C, Ho, Wo).total * (size_t)nstreams;
+}
+
+extern "C" size_t mog_stn_batch_host_workspace_bytes(int64_t chunk, int T, int Hs, int Ws, int C, int Ho, int Wo, int nstreams) {
+    if (chunk <= 0 || T <= 0 || Hs <= 0 || Ws <= 0 || C <= 0 || Ho <= 0 || Wo <= 0 || nstreams <= 0) return 0;
+    return host_chunk_layout(chunk, T, Hs, Ws, C, Ho, Wo).total * (size_t)nstreams;
 }
 
 #define MOG_CUDA_TRY(expr)                                                \
@@ -380,16 +386,20 @@ extern "C" size_t mog_stn_host_workspace_bytes(int64_t chunk, int Hs, int Ws, in
         }                                                                 \
     } while (0)
 
-extern "C" int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, const float* gout_h, float* out_h,
-                                    float* dU_h, float* dtheta_h, int64_t B, int Hs, int Ws, int C, int Ho, int Wo,
-                                    int64_t chunk, void* workspace_d, size_t workspace_bytes, void* const* streams,
-                                    int nstreams) {
-    if (int rc = check_dims(B, Hs, Ws, C, Ho, Wo, 1)) return rc;
-    MOG_REQUIRE(chunk > 0 && nstreams > 0 && nstreams <= 16, MOG_ERR_DIM, "fwd_bwd_host: chunk=%lld nstreams=%d", (long long)chunk, nstreams);
+// batch_transformer form (air/transformer.py:178-195) on host buffers: every source image is uploaded ONCE for its T
+// transforms, dU is accumulated over them on the device and downloaded once (or not at all: the AIR read site asks for
+// dtheta only, air_number_bbox_location.py:534-542).  Outputs are ordered like the reference's: index b*T + t.
+extern "C" int mog_stn_batch_fwd_bwd_host(const float* U_h, const float* thetas_h, const float* gout_h, float* out_h, float* dU_h,
+                                          float* dtheta_h, int64_t B, int T, int Hs, int Ws, int C, int Ho, int Wo, int64_t chunk,
+                                          void* workspace_d, size_t workspace_bytes, void* const* streams, int nstreams) {
+    MOG_REQUIRE(T >= 1, MOG_ERR_DIM, "batch_fwd_bwd_host: T=%d", T);
+    if (int rc = check_dims(B * T, Hs, Ws, C, Ho, Wo, T)) return rc;
+    MOG_REQUIRE(chunk > 0 && nstreams > 0 && nstreams <= 16, MOG_ERR_DIM, "batch_fwd_bwd_host: chunk=%lld nstreams=%d", (long long)chunk, nstreams);
     if (B == 0) return MOG_OK;
-    MOG_REQUIRE(U_h && theta_h && gout_h && out_h && workspace_d && streams, MOG_ERR_NULL, "fwd_bwd_host: NULL pointer");
-    const HostChunkLayout l = host_chunk_layout(chunk, Hs, Ws, C, Ho, Wo);
-    MOG_REQUIRE(workspace_bytes >= l.total * (size_t)nstreams, MOG_ERR_DIM, "fwd_bwd_host: workspace %zu B < required %zu B",
+    MOG_REQUIRE(U_h && thetas_h && out_h && workspace_d && streams, MOG_ERR_NULL, "batch_fwd_bwd_host: NULL pointer");
+    MOG_REQUIRE(gout_h || (!dU_h && !dtheta_h), MOG_ERR_NULL, "batch_fwd_bwd_host: gradients requested without gout");
+    const HostChunkLayout l = host_chunk_layout(chunk, T, Hs, Ws, C, Ho, Wo);
+    MOG_REQUIRE(workspace_bytes >= l.total * (size_t)nstreams, MOG_ERR_DIM, "batch_fwd_bwd_host: workspace %zu B < required %zu B",
                 workspace_bytes, l.total * (size_t)nstreams);
     const size_t imU = (size_t)Hs * Ws * C, imO = (size_t)Ho * Wo * C;
     const Geo g = make_geo(Hs, Ws, C, Ho, Wo);
@@ -404,25 +414,34 @@ extern "C" int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, cons
         float* dout = (float*)(base + l.out);
         float* ddU = (float*)(base + l.dU);
         float* ddth = (float*)(base + l.dtheta);
+        const bool bwd = dU_h || dtheta_h;
         MOG_CUDA_TRY(cudaMemcpyAsync(dUin, U_h + b0 * imU, nb * imU * sizeof(float), cudaMemcpyHostToDevice, st));
-        MOG_CUDA_TRY(cudaMemcpyAsync(dth, theta_h + b0 * 6, nb * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-        MOG_CUDA_TRY(cudaMemcpyAsync(dgo, gout_h + b0 * imO, nb * imO * sizeof(float), cudaMemcpyHostToDevice, st));
+        MOG_CUDA_TRY(cudaMemcpyAsync(dth, thetas_h + b0 * T * 6, nb * T * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+        if (bwd) MOG_CUDA_TRY(cudaMemcpyAsync(dgo, gout_h + b0 * T * imO, nb * T * imO * sizeof(float), cudaMemcpyHostToDevice, st));
         FwdArgs fa{};
-        fa.U = dUin; fa.theta = dth; fa.out = dout; fa.B = nb; fa.u_div = 1; fa.g = g;
+        fa.U = dUin; fa.theta = dth; fa.out = dout; fa.B = nb * T; fa.u_div = T; fa.g = g;
         if (int rc = launch_fwd<false>(fa, st)) return rc;
-        MOG_CUDA_TRY(cudaMemcpyAsync(out_h + b0 * imO, dout, nb * imO * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (dU_h || dtheta_h) {
+        MOG_CUDA_TRY(cudaMemcpyAsync(out_h + b0 * T * imO, dout, nb * T * imO * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (bwd) {
             BwdArgs ba{};
             ba.U = dUin; ba.theta = dth; ba.gout = dgo; ba.dU = dU_h ? ddU : nullptr; ba.dtheta = dtheta_h ? ddth : nullptr;
-            ba.Bsrc = nb; ba.u_div = 1; ba.g = g;
+            ba.Bsrc = nb; ba.u_div = T; ba.g = g;
             if (int rc = launch_bwd<false>(ba, st)) return rc;
             if (dU_h)
                 MOG_CUDA_TRY(cudaMemcpyAsync(dU_h + b0 * imU, ddU, nb * imU * sizeof(float), cudaMemcpyDeviceToHost, st));
             if (dtheta_h)
-                MOG_CUDA_TRY(cudaMemcpyAsync(dtheta_h + b0 * 6, ddth, nb * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                MOG_CUDA_TRY(cudaMemcpyAsync(dtheta_h + b0 * T * 6, ddth, nb * T * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
     }
     const int used = k < nstreams ? k : nstreams;
     for (int i = 0; i < used; ++i) MOG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)streams[i]));
     return MOG_OK;
+}
+
+extern "C" int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, const float* gout_h, float* out_h, float* dU_h,
+                                    float* dtheta_h, int64_t B, int Hs, int Ws, int C, int Ho, int Wo, int64_t chunk,
+                                    void* workspace_d, size_t workspace_bytes, void* const* streams, int nstreams) {
+    MOG_REQUIRE(B == 0 || gout_h, MOG_ERR_NULL, "fwd_bwd_host: NULL pointer");
+    return mog_stn_batch_fwd_bwd_host(U_h, theta_h, gout_h, out_h, dU_h, dtheta_h, B, 1, Hs, Ws, C, Ho, Wo, chunk, workspace_d,
+                                      workspace_bytes, streams, nstreams);
 }

@@ -371,6 +371,67 @@ def _load_reference_graph_run(name):
     return g, cfg, model, params, mp
 
 
+def _load_generation_run(name):
+    """weights / noise / outputs of the reference's generation graph run on the torch TF shim (tests/golden/make_golden_generation.py)"""
+    from mog_asr_b200.air.model import AIRConfig
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"graph_generation_{name}.npz"))
+    c = eval(str(g["cfg"]), {"__builtins__": {}})
+    cfg = AIRConfig(canvas_size=c["canvas"], windows_size=c["ws"], max_steps=c["max_steps"], rnn_units=c["rnn"], vae_latent_dimensions=c["lat"],
+                    vae_recognition_units=c["rec"], vae_generative_units=c["gen"], scale_hidden_units=c["hid"], shift_hidden_units=c["hid"],
+                    z_pres_hidden_units=c["hid"], z_pres_temperature=c["zt"], constrains_num=c["counts"],
+                    constrains_area_minmax=tuple(c["minmax"]), fix_steps=c["counts"][0] if len(c["counts"]) == 1 else None)
+    model = AIRModel(cfg, ops=OracleOps()).double()
+    P = "air/air_model/"
+    dense = lambda tfname, lyr, w="kernel", b="bias": {lyr + ".weight": (P + tfname + "/" + w, True), lyr + ".bias": (P + tfname + "/" + b, False)}
+    mp = {"gen_cell.kernel": (P + "gen_rnn_running/lstm_cell/kernel", False), "gen_cell.bias": (P + "gen_rnn_running/lstm_cell/bias", False)}
+    for tfl, mine in (("dense", "hm"), ("dense_1", "m"), ("dense_2", "hv"), ("dense_3", "v")):
+        mp.update(dense(f"gen_shift/{tfl}", f"gen_shift.{mine}"))
+    for i in (1, 2):
+        mp.update(dense(f"vae/generative_{i}", f"vae_gen.{i - 1}", "weights", "biases"))
+    mp.update(dense("vae/gen_mean", "vae_gen_mean", "weights", "biases"))
+    if cfg.fix_steps is None:
+        mp.update(dense("z_pres/prior/dense", "z_prior_h")); mp.update(dense("z_pres/prior/dense_1", "z_prior"))
+    params = dict(model.named_parameters())
+    with torch.no_grad():                                          # (the generation graph uses the generative half of the weights only)
+        for n, (tfn, tr) in mp.items():
+            w = torch.tensor(g["w:" + tfn])
+            params[n].copy_(w.t() if tr else w)
+    return g, cfg, model
+
+
+@pytest.mark.parametrize("name", ["learned_prior", "fix_steps"])
+def test_generate_equals_the_reference_generation_graph_run_on_the_tf_shim(name):
+    """``AIRModel.generate`` against the reference's own ``_create_generation`` (with its ``vae_generation``, ``concrete.py`` and
+    ``transformer.py``) executed on the torch TF shim in float64 with the same weights and injected noise: same trip count of the
+    data-dependent loop, same object counts, same write transforms (the constant-scale override of :1203-1205) and the same
+    generated canvases (Bernoulli-binarised windows written through the sampler)."""
+    g, cfg, model = _load_generation_run(name)
+    noise = lambda kind, step, shape: torch.tensor(g["noise_" + kind][step]).reshape(shape)
+    out = model.generate(g["samples"].shape[0], noise=noise)
+    assert out["steps"] == int(g["steps"])
+    assert np.array_equal(out["num"].numpy(), g["num"])
+    np.testing.assert_allclose(out["thetas"].numpy(), g["thetas"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out["samples"].numpy(), g["samples"], atol=2e-6)      # fp32-rounded sampler constants of the oracle
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["learned_prior", "fix_steps"])
+def test_cuda_generate_equals_the_reference_generation_graph(name, cuda_device):
+    """The product path of the generation graph (fp32, the fused write + composite kernel) with the golden weights and noise:
+    same trip count and counts, canvases within fp32 rounding of the reference run."""
+    g, cfg, model64 = _load_generation_run(name)
+    model = AIRModel(cfg, ops=CudaOps()).to(cuda_device)
+    with torch.no_grad():
+        for (n, p), (_, q) in zip(model.named_parameters(), model64.named_parameters()):
+            p.copy_(q.to(torch.float32))
+    noise = lambda kind, step, shape: torch.tensor(g["noise_" + kind][step], dtype=torch.float32, device=cuda_device).reshape(shape)
+    out = model.generate(g["samples"].shape[0], noise=noise)
+    assert out["steps"] == int(g["steps"])
+    assert np.array_equal(out["num"].cpu().numpy(), g["num"])
+    np.testing.assert_allclose(out["thetas"].cpu().numpy(), g["thetas"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(out["samples"].cpu().numpy(), g["samples"], atol=1e-5)
+
+
 @pytest.mark.parametrize("name", ["c2", "c3", "all"])
 def test_rehosted_model_equals_the_reference_graph_run_on_the_tf_shim(name):
     """The reference's WHOLE training graph (``AIRModel._create_model`` with its own vae / concrete / transformer files) was

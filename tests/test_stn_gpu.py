@@ -277,6 +277,30 @@ def test_host_buffer_entry_point_matches_device_path(cuda_device):
 
 
 @pytest.mark.gpu
+def test_batch_host_entry_point_matches_batch_transformer(cuda_device):
+    """mog_stn_batch_fwd_bwd_host: the batch_transformer form on host buffers (every source image uploaded once for its T
+    transforms, dU summed over them) -- same bits as batch_transformer + autograd on the device, ragged last chunk, and the
+    dtheta-only form of the AIR read site."""
+    from mog_asr_b200.host_api import HostSampler
+    rng = np.random.default_rng(78)
+    B, T = 150, 4                                # chunk 64 -> two full chunks and a ragged one
+    U = torch.from_numpy(rng.random((B, 50, 50, 1), dtype=np.float32)).pin_memory()
+    s, x, y = synth.sxy_prior_like(B * T, seed=9)
+    th = torch.from_numpy(synth.theta_read(s, x, y).reshape(B, T, 6)).pin_memory()
+    g = torch.from_numpy(rng.standard_normal((B, T, 28, 28, 1), dtype=np.float32)).pin_memory()
+    hs = HostSampler(cuda_device, (50, 50), (28, 28), 1, chunk=64, nstreams=3, transforms=T)
+    out, dU, dth = hs.batch_fwd_bwd(U, th, g)
+    Ud, td = U.to(cuda_device).requires_grad_(True), th.to(cuda_device).requires_grad_(True)
+    o = M.batch_transformer(Ud, td, (28, 28))
+    o.backward(g.reshape(B * T, 28, 28, 1).to(cuda_device))
+    assert torch.equal(out, o.detach().cpu()) and torch.equal(dU, Ud.grad.cpu()) and torch.equal(dth, td.grad.cpu())
+    out2, dU2, dth2 = hs.batch_fwd_bwd(U, th, g, need_dU=False)
+    assert dU2 is None and torch.equal(out2, out) and torch.equal(dth2, dth)
+    out3, dU3, dth3 = hs.batch_fwd_bwd(U, th)    # forward only
+    assert dU3 is None and dth3 is None and torch.equal(out3, out)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("src,dst", [((131, 127), (33, 29)), ((33, 29), (131, 127)), ((256, 256), (64, 64)), ((64, 64), (256, 256)),
                                      ((90, 93), (90, 93))])
 def test_large_images_every_element_written(cuda_device, src, dst):
