@@ -563,6 +563,10 @@ def train_section(a, dev, world, pg, rank):
     r = bench_train.run("C4", dev, steps=10, warmup=3, process_group=pg, always_max_steps=True, graph=True)
     out["C4_global4096"] = r
     if world > 1:
+        try:   # multi-GPU correctness on this very hardware: all-reduced gradient vs the single-process global-batch gradient
+            out["dp_check"] = bench_train.dp_check(dev, pg)
+        except Exception as e:
+            out["dp_check"] = dict(error=f"{type(e).__name__}: {e}")
         # the same model with the per-GPU work held at 4096 images (weak scaling): separates the all-reduce cost from
         # the fixed per-step launch chain that bounds the strong-scaling line above
         out["C4_weak_4096_per_gpu"] = bench_train.run("C4", dev, steps=10, warmup=3, process_group=pg, always_max_steps=True,

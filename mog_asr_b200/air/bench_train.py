@@ -77,3 +77,67 @@ def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=F
                 per_rank_batch=local, n_gpus=world, mean_loop_steps=T / steps, grad_floats=tr.num_gradient_floats(),
                 mode=("CUDA graph, fixed max_steps" if graph else "eager, fixed max_steps") if always_max_steps
                 else "eager, reference loop condition (host-checked any)")
+
+
+class GlobalSeededNoise:
+    """``noise(kind, step, shape)`` for data-parallel checks: the draw for the GLOBAL batch comes from a CPU generator seeded by
+    (seed, kind, step) and the rank's rows are cut out, so that any sharding of the batch sees the same numbers."""
+    _KIND = {"shift": 1, "scale": 2, "vae": 3, "concrete": 4}
+
+    def __init__(self, seed, global_batch, lo, hi, device):
+        self.seed, self.B, self.lo, self.hi, self.device = seed, global_batch, lo, hi, device
+
+    def __call__(self, kind, step, shape):
+        g = torch.Generator().manual_seed(self.seed * 1000 + self._KIND[kind] * 100 + step)
+        full = (self.B,) + tuple(shape[1:])
+        t = torch.rand(full, generator=g).clamp_(1e-4, 1 - 1e-4) if kind == "concrete" else torch.randn(full, generator=g)
+        return t[self.lo:self.hi].to(self.device)
+
+
+def dp_check(device, process_group, global_batch=64, seed=31, ops_factory=None):
+    """Multi-GPU correctness of the training step on the hardware it runs on ("1/2/4/8-GPU gradient equality
+    vs 1-GPU at the same global batch"): config C2 (``-dn 13 -gm 100 -gne 10``: the ``[T]`` column-sum all-reduce of the marginal
+    count penalty runs, air_number_bbox_location.py:982), ``global_batch`` images sharded over the ranks, identical noise per
+    image on any sharding.  The all-reduced flat gradient is compared with the single-process gradient of the whole batch
+    (computed on every rank), per parameter tensor, relative to that tensor's largest entry.  (``ops_factory(process_group,
+    global_batch)`` replaces the product operators -- the CPU test of this function runs it over gloo.)  A second pass runs the reference's
+    loop form (``while any(stop_sum < thr)``, :386-390) and checks that every rank executed the same number of iterations as
+    the single process (the one-flag ``any`` all-reduce)."""
+    world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+    flags = CONFIGS["C2"][0]
+    lo, hi = rank * global_batch // world, (rank + 1) * global_batch // world
+    out = dict(config="C2 flags, global batch %d over %d ranks" % (global_batch, world))
+    for mode, amx in (("fixed_trip_count", True), ("reference_loop", False)):
+        cfg = config_from_flags(always_max_steps=amx, **flags)
+        images = synthetic_batch(cfg, global_batch, 4242, device)            # same canvases on every rank (seeded feeder)
+        mk = (lambda pg: None) if ops_factory is None else (lambda pg: ops_factory(pg, global_batch))
+        dp = Trainer(cfg, device, process_group=process_group, global_batch=global_batch, seed=seed, ops=mk(process_group))
+        o_dp = dp.forward_backward(images[lo:hi], noise=GlobalSeededNoise(7, global_batch, lo, hi, device))
+        dp.reduce_gradients()
+        one = Trainer(cfg, device, process_group=None, global_batch=global_batch, seed=seed, ops=mk(None))
+        o_one = one.forward_backward(images, noise=GlobalSeededNoise(7, global_batch, 0, global_batch, device))
+        worst, worst_name, off = 0.0, "", 0
+        for name, p in one.model.named_parameters():
+            n = p.numel()
+            a, b = one.flat_grad[off:off + n], dp.flat_grad[off:off + n]
+            off += n
+            scale = float(a.abs().max())
+            if scale > 0:
+                d = float((a - b).abs().max()) / scale
+                if d > worst:
+                    worst, worst_name = d, name
+        local = (o_dp["loss"].detach() - o_dp["margin"]).reshape(1).clone()
+        dist.all_reduce(local, group=process_group)
+        loss_dp = float(local) + float(o_dp["margin"])
+        steps = torch.tensor([o_dp["steps"]], device=device)
+        gathered = [torch.zeros_like(steps) for _ in range(world)]
+        dist.all_gather(gathered, steps, group=process_group)
+        trip = [int(t) for t in gathered]
+        w = torch.tensor([worst], device=device, dtype=torch.float64)
+        dist.all_reduce(w, op=dist.ReduceOp.MAX, group=process_group)
+        out[mode] = dict(max_rel_diff=float(w), worst_parameter=worst_name, loss_dp=loss_dp, loss_single=float(o_one["loss"]),
+                         loss_diff=abs(loss_dp - float(o_one["loss"])), trip_counts=trip, trip_count_single=int(o_one["steps"]),
+                         same_trip_count=len(set(trip)) == 1 and trip[0] == int(o_one["steps"]))
+    out["max_rel_diff"] = max(out[m]["max_rel_diff"] for m in ("fixed_trip_count", "reference_loop"))
+    out["ok"] = bool(out["max_rel_diff"] <= 2e-3 and all(out[m]["same_trip_count"] for m in ("fixed_trip_count", "reference_loop")))
+    return out

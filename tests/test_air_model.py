@@ -155,6 +155,63 @@ def test_data_parallel_gradients_equal_single_process_gloo():
     assert float((got[finite] - ref[finite]).abs().max()) <= 2e-3 * float(scale)
 
 
+def _gloo_dp_check_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from mog_asr_b200.air import bench_train
+    torch.set_num_threads(1)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = bench_train.dp_check("cpu", dist.group.WORLD, global_batch=8,
+                                 ops_factory=lambda pg, gb: OracleOps(process_group=pg, global_batch=gb))
+        if rank == 0:
+            ret["dp_check"] = r
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_check_of_the_bench_over_gloo():
+    """bench.py's ``train.dp_check`` (gradient equality, loss, trip counts of both loop forms) run on two CPU ranks over gloo
+    with the oracle's operators: exercises the code the driver runs under NCCL at N > 1."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_gloo_dp_check_worker, args=(2, port, ret), nprocs=2, join=True)
+    r = ret["dp_check"]
+    assert r["ok"], r
+    for mode in ("fixed_trip_count", "reference_loop"):
+        assert r[mode]["loss_diff"] <= 1e-3 * abs(r[mode]["loss_single"]), r[mode]
+
+
+def _nccl_dp_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from mog_asr_b200.air import bench_train
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        r = bench_train.dp_check(dev, dist.group.WORLD, global_batch=32)
+        if rank == 0:
+            ret["dp_check"] = r
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_data_parallel_gradients_equal_single_process_nccl(cuda_device):
+    """Two ranks on two GPUs over NCCL with the product operators: the all-reduced gradient equals the single-process gradient of
+    the whole batch (including the [T] column-sum all-reduce of the marginal count penalty), and the reference's loop form runs
+    the same trip count on every rank (the one-flag ``any`` all-reduce).  Needs two devices; bench.py records the same check
+    at every N > 1 (``train.dp_check``)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices (recorded by bench.py at N > 1 instead)")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_dp_worker, args=(2, port, ret), nprocs=2, join=True)
+    r = ret["dp_check"]
+    assert r["ok"], r
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("flags", [dict(data="mnist", dn="13", gm=100.0, gne=10.0),
                                    dict(data="sprites", dn="3", ds="bbox20k", gb=1.0, gs=10.0, ga=20.0)])
