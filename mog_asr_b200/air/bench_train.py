@@ -100,22 +100,31 @@ def dp_check(device, process_group, global_batch=64, seed=31, ops_factory=None):
     count penalty runs, air_number_bbox_location.py:982), ``global_batch`` images sharded over the ranks, identical noise per
     image on any sharding.  The all-reduced flat gradient is compared with the single-process gradient of the whole batch
     (computed on every rank), per parameter tensor, relative to that tensor's largest entry.  (``ops_factory(process_group,
-    global_batch)`` replaces the product operators -- the CPU test of this function runs it over gloo.)  A second pass runs the reference's
-    loop form (``while any(stop_sum < thr)``, :386-390) and checks that every rank executed the same number of iterations as
-    the single process (the one-flag ``any`` all-reduce)."""
+    global_batch)`` replaces the product operators -- the CPU test of this function runs it over gloo.)
+
+    Two reconstruction terms: the verdict (``max_rel_diff``, ``ok``) uses a squared-error term through the same graph, because the
+    reference's cross-entropy (:954-959) has gradients of 1e10 wherever the canvas is 0 under an object pixel: the library GEMMs
+    pick different tiles for a shard than for the whole batch, their sums differ in the last bit, and that term amplifies the
+    difference to O(0.1) of a gradient entry in ANY fp32 implementation (tests/test_air_model.py has the same split).  The
+    cross-entropy figures are reported beside it (``with_reference_cross_entropy``), not judged.
+
+    A second pass runs the reference's loop form (``while any(stop_sum < thr)``, :386-390) and checks that every rank executed
+    the same number of iterations as the single process (the one-flag ``any`` all-reduce)."""
     world, rank = dist.get_world_size(process_group), dist.get_rank(process_group)
     flags = CONFIGS["C2"][0]
     lo, hi = rank * global_batch // world, (rank + 1) * global_batch // world
     out = dict(config="C2 flags, global batch %d over %d ranks" % (global_batch, world))
-    for mode, amx in (("fixed_trip_count", True), ("reference_loop", False)):
+    mse = lambda x, r: ((x - r) ** 2).sum(1) * 50.0
+    mk = (lambda pg: None) if ops_factory is None else (lambda pg: ops_factory(pg, global_batch))
+
+    def compare(amx, recon_fn):
         cfg = config_from_flags(always_max_steps=amx, **flags)
         images = synthetic_batch(cfg, global_batch, 4242, device)            # same canvases on every rank (seeded feeder)
-        mk = (lambda pg: None) if ops_factory is None else (lambda pg: ops_factory(pg, global_batch))
         dp = Trainer(cfg, device, process_group=process_group, global_batch=global_batch, seed=seed, ops=mk(process_group))
-        o_dp = dp.forward_backward(images[lo:hi], noise=GlobalSeededNoise(7, global_batch, lo, hi, device))
+        o_dp = dp.forward_backward(images[lo:hi], noise=GlobalSeededNoise(7, global_batch, lo, hi, device), recon_loss_fn=recon_fn)
         dp.reduce_gradients()
         one = Trainer(cfg, device, process_group=None, global_batch=global_batch, seed=seed, ops=mk(None))
-        o_one = one.forward_backward(images, noise=GlobalSeededNoise(7, global_batch, 0, global_batch, device))
+        o_one = one.forward_backward(images, noise=GlobalSeededNoise(7, global_batch, 0, global_batch, device), recon_loss_fn=recon_fn)
         worst, worst_name, off = 0.0, "", 0
         for name, p in one.model.named_parameters():
             n = p.numel()
@@ -135,9 +144,14 @@ def dp_check(device, process_group, global_batch=64, seed=31, ops_factory=None):
         trip = [int(t) for t in gathered]
         w = torch.tensor([worst], device=device, dtype=torch.float64)
         dist.all_reduce(w, op=dist.ReduceOp.MAX, group=process_group)
-        out[mode] = dict(max_rel_diff=float(w), worst_parameter=worst_name, loss_dp=loss_dp, loss_single=float(o_one["loss"]),
-                         loss_diff=abs(loss_dp - float(o_one["loss"])), trip_counts=trip, trip_count_single=int(o_one["steps"]),
-                         same_trip_count=len(set(trip)) == 1 and trip[0] == int(o_one["steps"]))
+        return dict(max_rel_diff=float(w), worst_parameter=worst_name, loss_dp=loss_dp, loss_single=float(o_one["loss"].detach()),
+                    loss_rel_diff=abs(loss_dp - float(o_one["loss"].detach())) / max(abs(float(o_one["loss"].detach())), 1e-30),
+                    trip_counts=trip, trip_count_single=int(o_one["steps"]),
+                    same_trip_count=len(set(trip)) == 1 and trip[0] == int(o_one["steps"]))
+
+    for mode, amx in (("fixed_trip_count", True), ("reference_loop", False)):
+        out[mode] = compare(amx, mse)
+    out["with_reference_cross_entropy"] = compare(True, None)
     out["max_rel_diff"] = max(out[m]["max_rel_diff"] for m in ("fixed_trip_count", "reference_loop"))
     out["ok"] = bool(out["max_rel_diff"] <= 2e-3 and all(out[m]["same_trip_count"] for m in ("fixed_trip_count", "reference_loop")))
     return out

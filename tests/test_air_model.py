@@ -179,7 +179,7 @@ def test_dp_check_of_the_bench_over_gloo():
     r = ret["dp_check"]
     assert r["ok"], r
     for mode in ("fixed_trip_count", "reference_loop"):
-        assert r[mode]["loss_diff"] <= 1e-3 * abs(r[mode]["loss_single"]), r[mode]
+        assert r[mode]["loss_rel_diff"] <= 1e-5, r[mode]
 
 
 def _nccl_dp_worker(rank, world, port, ret):
