@@ -16,6 +16,7 @@
 #include "mog_stn_warp.cuh"
 #include "mog_stn_bwd.cuh"
 #include "mog_stn_bwd_tma.cuh"
+#include "mog_stn_bwd_cta.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -153,6 +154,15 @@ static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
     return MOG_OK;
 }
 
+template <bool COMPOSITE>
+static int launch_bwd_stream(const BwdArgs& a, cudaStream_t st) {
+    // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
+    const int nxc = (a.g.Ws + 31) / 32;
+    if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);
+    if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st);
+    return launch_bwd_nxc<COMPOSITE, 4>(a, st);
+}
+
 template <bool COMPOSITE, int NJC>
 static int launch_bwd_group(const BwdArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)kWarpsPerCta * bwd2_warp_smem_words(a.g) * sizeof(int) + (a.coop_zero == 2 ? kZeroBytes : 0);
@@ -223,16 +233,64 @@ static int launch_bwd_tma(const BwdArgs& a, cudaStream_t st, bool* launched) {
     return MOG_OK;
 }
 
-// MOG_BWD_IMPL selects the separable-theta backward: "stream" (row-streaming gather form), "group" (grouped gather form,
-// register loads), "tma" (grouped form, TMA-staged, where eligible; else "group").  Read once.
-enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2 };
+// Write direction, one CTA per image (mog_stn_bwd_cta.cuh): source window <= 64 columns, <= 4096 pixels, one channel.
+static void bwd_cta_shape(const Geo& g, int* rb, int* nbuf) {
+    // measured on B200 (profiles/r02_write_bwd_variants.md): windows of 64 x 64 run best with 8-row batches and one buffer,
+    // smaller windows (more CTAs per SM) with the double-buffered form; MOG_CTA_RB / MOG_CTA_NBUF override for experiments
+    static const int e_rb = env_flag("MOG_CTA_RB", 0), e_nb = env_flag("MOG_CTA_NBUF", 0);
+    *rb = e_rb ? e_rb : 8;
+    *nbuf = e_nb ? e_nb : (g.S > 1024 ? 1 : 2);
+}
+
+static bool bwd_cta_eligible(const BwdArgs& a) {
+    const Geo& g = a.g;
+    int rb, nbuf;
+    bwd_cta_shape(g, &rb, &nbuf);
+    return g.C == 1 && a.u_div == 1 && g.Ws <= kCtaMaxWs && g.S <= kTmaMaxSrc && g.Wo < 65536 && a.Bsrc < (1ll << 31) &&
+           (size_t)bwd_cta_layout(g, rb, nbuf).total <= (size_t)kMaxSmemBytes;
+}
+
+template <bool COMPOSITE, int RB, int NBUF>
+static int launch_bwd_cta_shape(const BwdArgs& a, cudaStream_t st) {
+    static const int tma_on = env_flag("MOG_BWD_TMA", 1);
+    CUtensorMap tmU;
+    memset(&tmU, 0, sizeof(tmU));
+    // the source window arrives by one tensor copy when its rows are 16-byte multiples; else by coalesced loads
+    const int use_tma = tma_on && a.g.Ws % 4 == 0 && (reinterpret_cast<uintptr_t>(a.U) & 15) == 0 &&
+                        make_tmap3(&tmU, a.U, a.g.Ws, a.g.Hs, a.Bsrc, a.g.Ws, a.g.Hs);
+    const size_t smem = (size_t)bwd_cta_layout(a.g, RB, NBUF).total;
+    if (int rc = set_smem(stn_bwd_cta_kernel<COMPOSITE, RB, NBUF>, smem)) return rc;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_bwd_cta_kernel<COMPOSITE, RB, NBUF>, kCtaThreads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    stn_bwd_cta_kernel<COMPOSITE, RB, NBUF><<<grid_for(a.Bsrc, per_sm), kCtaThreads, smem, st>>>(tmU, a, use_tma);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_cta_kernel");
+    return MOG_OK;
+}
+
+template <bool COMPOSITE>
+static int launch_bwd_cta(const BwdArgs& a, cudaStream_t st) {
+    int rb, nbuf;
+    bwd_cta_shape(a.g, &rb, &nbuf);
+    if (rb == 4) return nbuf == 2 ? launch_bwd_cta_shape<COMPOSITE, 4, 2>(a, st) : launch_bwd_cta_shape<COMPOSITE, 4, 1>(a, st);
+    return nbuf == 2 ? launch_bwd_cta_shape<COMPOSITE, 8, 2>(a, st) : launch_bwd_cta_shape<COMPOSITE, 8, 1>(a, st);
+}
+
+// MOG_BWD_IMPL selects the separable-theta backward (read once).  Default "auto": the CTA-per-image kernel where it is
+// eligible and measured faster (write direction onto outputs >= 192 columns wide: -25 ... -43 % on the 256-wide cells, a
+// tie at 128, slower below), the warp-per-image streaming kernel everywhere else.  "stream" / "cta" force one of the two
+// (cta falls back where ineligible); "group" (grouped gather form, register loads) and "tma" (grouped form, source and
+// gradient tiles staged by TMA) are the two experimental formulations kept for comparison (slower, see profiles/).
+enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2, kBwdCta = 3, kBwdAuto = 4 };
 static BwdImpl bwd_impl() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("MOG_BWD_IMPL");
-        v = kBwdStream;
+        v = kBwdAuto;
+        if (e && strcmp(e, "stream") == 0) v = kBwdStream;
         if (e && strcmp(e, "group") == 0) v = kBwdGroup;
         if (e && strcmp(e, "tma") == 0) v = kBwdTma;
+        if (e && strcmp(e, "cta") == 0) v = kBwdCta;
     }
     return (BwdImpl)v;
 }
@@ -243,6 +301,10 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     const BwdImpl impl = bwd_impl();
+    if (impl == kBwdCta || impl == kBwdAuto) {
+        if (bwd_cta_eligible(a) && (impl == kBwdCta || a.g.Wo >= 192)) return launch_bwd_cta<COMPOSITE>(a, st);
+        return launch_bwd_stream<COMPOSITE>(a, st);
+    }
     if (impl == kBwdTma && bwd_tma_eligible(a)) {
         bool launched = false;
         if (int rc = launch_bwd_tma<COMPOSITE>(a, st, &launched)) return rc;
@@ -253,11 +315,7 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
         if (a.g.Wo <= 32) return launch_bwd_group<COMPOSITE, 1>(a, st);
         return launch_bwd_group<COMPOSITE, 2>(a, st);
     }
-    // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
-    const int nxc = (a.g.Ws + 31) / 32;
-    if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);
-    if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st);
-    return launch_bwd_nxc<COMPOSITE, 4>(a, st);
+    return launch_bwd_stream<COMPOSITE>(a, st);
 }
 
 }  // namespace mog
