@@ -17,6 +17,7 @@
 #include "mog_stn_bwd.cuh"
 #include "mog_stn_bwd_tma.cuh"
 #include "mog_stn_bwd_cta.cuh"
+#include "mog_stn_bwd_rd.cuh"
 
 #include <cudaTypedefs.h>
 
@@ -276,6 +277,23 @@ static int launch_bwd_cta(const BwdArgs& a, cudaStream_t st) {
     return nbuf == 2 ? launch_bwd_cta_shape<COMPOSITE, 8, 2>(a, st) : launch_bwd_cta_shape<COMPOSITE, 8, 1>(a, st);
 }
 
+// Read direction with dU (mog_stn_bwd_rd.cuh): large source, glimpse-sized output, fill and arithmetic in different warps.
+static bool bwd_rd_eligible(const BwdArgs& a) {
+    const Geo& g = a.g;
+    return g.C == 1 && a.u_div == 1 && a.dU != nullptr && (long long)g.S >= MOG_COOP_ZERO_MIN_FLOATS && g.Wo <= 128 &&
+           g.Ws + 2 <= 64 * kRdNXCW && g.Wo < 65536 && a.Bsrc < (1ll << 31) && (size_t)bwd_rd_layout(g).total <= (size_t)kMaxSmemBytes;
+}
+
+static int launch_bwd_rd(const BwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)bwd_rd_layout(a.g).total;
+    if (int rc = set_smem(stn_bwd_rd_kernel, smem)) return rc;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_bwd_rd_kernel, kCtaThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    stn_bwd_rd_kernel<<<grid_for(a.Bsrc, per_sm), kCtaThreads, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_rd_kernel");
+    return MOG_OK;
+}
+
 // MOG_BWD_IMPL selects the separable-theta backward (read once).  Default "auto": the CTA-per-image kernel where it is
 // eligible and measured faster (write direction onto outputs >= 192 columns wide: -25 ... -43 % on the 256-wide cells, a
 // tie at 128, slower below), the warp-per-image streaming kernel everywhere else.  "stream" / "cta" force one of the two
@@ -302,6 +320,8 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     const BwdImpl impl = bwd_impl();
     if (impl == kBwdCta || impl == kBwdAuto) {
+        static const int rd_on = env_flag("MOG_BWD_RD", 0);
+        if (!COMPOSITE && rd_on && bwd_rd_eligible(a)) return launch_bwd_rd(a, st);
         if (bwd_cta_eligible(a) && (impl == kBwdCta || a.g.Wo >= 192)) return launch_bwd_cta<COMPOSITE>(a, st);
         return launch_bwd_stream<COMPOSITE>(a, st);
     }
