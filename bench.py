@@ -493,8 +493,62 @@ def aux_section(dev):
                           bytes_per_pixel=8, shape=[Bc, P])
     out["bce_bwd"] = dict(us=t_b, gbs=12.0 * Bc * P / (t_b * 1e-6) / 1e9, frac=12.0 * Bc * P / (t_b * 1e-6) / 1e9 / peak,
                           bytes_per_pixel=12, shape=[Bc, P])
+    out["general_affine"] = general_affine_section(dev, timeit)
     out["detection"] = detection_section(dev, timeit)
     out["dataset"] = dataset_section(dev, timeit)
+    return out
+
+
+def general_affine_section(dev, timeit):
+    """The cold path: rotated thetas (t01, t10 != 0) and three channels take the per-pixel forward and the scatter-form
+    backward (warp-aggregated red.global.add, csrc/mog_stn_warp.cuh: bwd_general_image).  Read direction 256x256 -> 64x64,
+    4096 canvases; the separable kernels on the same shapes are timed beside it."""
+    import torch
+    from mog_asr_b200 import _lib, synth
+    L = _lib.load()
+    peak, _ = peak_hbm()
+    B, cs, gs = 4096, 256, 64
+    s_, x_, y_ = synth.sxy_prior_like(B, seed=77)
+    phi = np.random.default_rng(78).uniform(-np.pi / 6, np.pi / 6, B).astype(np.float32)
+    rot = np.stack([s_ * np.cos(phi), -s_ * np.sin(phi), x_, s_ * np.sin(phi), s_ * np.cos(phi), y_], 1).astype(np.float32)
+    sep = synth.theta_read(s_, x_, y_)
+    out = {}
+    st = torch.cuda.current_stream(dev).cuda_stream
+    for C in (1, 3):
+        U = torch.rand((B, cs, cs, C), device=dev)
+        g = torch.randn((B, gs, gs, C), device=dev)
+        o, dU, dth = torch.empty((B, gs, gs, C), device=dev), torch.empty_like(U), torch.empty((B, 6), device=dev)
+        for name, th in (("rotated", rot), ("axis_aligned", sep)):
+            if name == "axis_aligned" and C != 1:
+                continue                                   # (C > 1 always takes the general path)
+            t = torch.tensor(th, device=dev)
+            f = lambda: _lib.check(L.mog_stn_forward(U.data_ptr(), t.data_ptr(), o.data_ptr(), B, cs, cs, C, gs, gs, 1, st), "fwd")
+            b = lambda: _lib.check(L.mog_stn_backward(U.data_ptr(), t.data_ptr(), g.data_ptr(), dU.data_ptr(), dth.data_ptr(), B, cs, cs, C,
+                                                      gs, gs, 1, st), "bwd")
+            tf_, tb_ = timeit(f, 5), timeit(b, 5)
+            out[f"{name}_C{C}"] = dict(fwd_us=tf_, bwd_us=tb_, glimpses_per_s_fwd_bwd=B / ((tf_ + tb_) * 1e-6),
+                                       bwd_write_gbs=4.0 * B * cs * cs * C / (tb_ * 1e-6) / 1e9,
+                                       bwd_frac_of_peak_by_dU_bytes=4.0 * B * cs * cs * C / (tb_ * 1e-6) / 1e9 / peak)
+        del U, g, o, dU
+        torch.cuda.empty_cache()
+    # magnifying direction (a 64 x 64 window written onto a 256 x 256 canvas, full-cover scale: ~3.6 output pixels per source
+    # pixel): the case warp aggregation is for -- every source pixel receives many lanes' contributions
+    s2, x2, y2 = synth.sxy_full_cover(B, seed=79)
+    inv = 1.0 / s2
+    rotw = np.stack([inv * np.cos(phi), inv * np.sin(phi), -(x2 * np.cos(phi) + y2 * np.sin(phi)) * inv,
+                     -inv * np.sin(phi), inv * np.cos(phi), (x2 * np.sin(phi) - y2 * np.cos(phi)) * inv], 1).astype(np.float32)
+    W = torch.rand((B, gs, gs, 1), device=dev)
+    gw = torch.randn((B, cs, cs, 1), device=dev)
+    ow, dW, dth = torch.empty((B, cs, cs, 1), device=dev), torch.empty_like(W), torch.empty((B, 6), device=dev)
+    t = torch.tensor(rotw, device=dev)
+    f = lambda: _lib.check(L.mog_stn_forward(W.data_ptr(), t.data_ptr(), ow.data_ptr(), B, gs, gs, 1, cs, cs, 1, st), "fwd")
+    b = lambda: _lib.check(L.mog_stn_backward(W.data_ptr(), t.data_ptr(), gw.data_ptr(), dW.data_ptr(), dth.data_ptr(), B, gs, gs, 1,
+                                              cs, cs, 1, st), "bwd")
+    tf_, tb_ = timeit(f, 3), timeit(b, 3)
+    out["rotated_write_full_cover_C1"] = dict(fwd_us=tf_, bwd_us=tb_, glimpses_per_s_fwd_bwd=B / ((tf_ + tb_) * 1e-6),
+                                              bwd_read_gbs=4.0 * B * cs * cs / (tb_ * 1e-6) / 1e9)
+    out["workload"] = (f"read {cs}x{cs} -> {gs}x{gs} and (write, full-cover scale) {gs}x{gs} -> {cs}x{cs}, {B} canvases, "
+                       "rotation uniform in +-30 degrees")
     return out
 
 

@@ -376,6 +376,12 @@ __device__ __forceinline__ void emit_px(char* p, float v, bool ok, bool first) {
 
 // General affine theta and/or several channels: warp-local zero fill of this image's dU, then L2 atomics
 // (red.global.add.f32) on its own lines; dtheta/dz by warp shuffles.  Out of line (cold path).
+// Warp-aggregated atomics were built and measured for this path in round 2 (neighbour hand-over of the right taps by one
+// shuffle + shuffle sums over runs of equal addresses, one reduction per run) and lost on B200 in both regimes:
+// rotated 256 -> 64 read (about one source pixel per output pixel) 439 us plain vs 554 us aggregated; rotated 64 -> 256
+// write at full-cover scale (3.6 output pixels per source pixel, the case aggregation is for) 7.2 ms plain vs 17.7 ms
+// aggregated (4096 images; bench.py aux_kernels.general_affine, profiles/r02_general_affine.md).  The L2 reduction units
+// absorb the duplicates faster than the warp can find them, so the plain per-lane form stays.
 template <bool COMPOSITE>
 __device__ __noinline__ void bwd_general_image(const float* __restrict__ Ub, float* __restrict__ dUb,
                                                const float* __restrict__ gb, float* __restrict__ dtheta_b,
