@@ -830,6 +830,10 @@ def run_sweep(a):
     torch.cuda.set_device(dev)
     peak, peak_src = peak_hbm()
     rows = []
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{a.tag or 'latest'}_sweep.json")))
+    except Exception:
+        traffic = {}
     for canvas in (50, 64, 128, 256):
         for glimpse in (28, 64):
             if glimpse >= canvas:
@@ -857,6 +861,13 @@ def run_sweep(a):
                            kernels={k: dict(us=kern_ms[k] * 1e3, alg_mb=ab[k] / 1e6, gbs=ab[k] / (kern_ms[k] * 1e-3) / 1e9,
                                             frac=ab[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds})
                 row["step_frac"] = row["step_alg_gbs"] / peak
+                tcell = traffic.get(f"{canvas}:{glimpse}:{regime}")
+                if tcell and tcell["cell"]["batch"] == c.batch:     # measured DRAM bytes per launch (tools/traffic_capture.py under ncu)
+                    for k in wl.kinds:
+                        row["kernels"][k]["traffic_mb"] = tcell["bytes_per_launch"][k] / 1e6
+                        row["kernels"][k]["frac_physical"] = tcell["bytes_per_launch"][k] / (kern_ms[k] * 1e-3) / 1e9 / peak
+                    row["step_physical_gbs"] = sum(tcell["bytes_per_launch"][k] for k in wl.kinds) * AIR_STEPS / (ms * 1e-3) / 1e9
+                    row["step_frac_physical"] = row["step_physical_gbs"] / peak
                 rows.append(row)
                 emit(row)
                 del wl

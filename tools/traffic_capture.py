@@ -9,6 +9,8 @@ Two modes:
             -k regex:'stn_(fwd|bwd)' --csv --log-file gpurun_out/traffic.csv python tools/traffic_capture.py run ...
     python tools/traffic_capture.py parse gpurun_out/traffic.csv --canvas ... > profiles/traffic_latest.json
         averages the two launches of every kind and records the commit the capture was taken at.
+    python tools/traffic_capture.py parse gpurun_out/traffic.csv --canvas ... --into profiles/traffic_r02_sweep.json
+        adds the cell to a multi-cell file (keys "canvas:glimpse:regime") that `bench.py --sweep` reads.
 """
 import argparse
 import csv
@@ -30,6 +32,7 @@ def main():
     p.add_argument("--glimpse", type=int, default=64)
     p.add_argument("--regime", default="prior")
     p.add_argument("--batch", type=int, default=16384)
+    p.add_argument("--into", default="")
     a = p.parse_args()
     if a.mode == "run":
         import torch
@@ -58,10 +61,19 @@ def main():
         b = sum(m[k][0] * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
         out[KINDS[n % 4]] += b / 2
     head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
-    json.dump(dict(source=f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over tools/traffic_capture.py "
-                          f"(two launches per kernel, averaged), taken at commit {head}",
-                   cell=dict(canvas=a.canvas, glimpse=a.glimpse, regime=a.regime, batch=a.batch),
-                   bytes_per_launch={k: int(v) for k, v in out.items()}), sys.stdout, indent=1)
+    rec = dict(source=f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over tools/traffic_capture.py "
+                      f"(two launches per kernel, averaged), taken at commit {head}",
+               cell=dict(canvas=a.canvas, glimpse=a.glimpse, regime=a.regime, batch=a.batch),
+               bytes_per_launch={k: int(v) for k, v in out.items()})
+    if a.into:
+        try:
+            allc = json.load(open(a.into))
+        except Exception:
+            allc = {}
+        allc[f"{a.canvas}:{a.glimpse}:{a.regime}"] = rec
+        json.dump(allc, open(a.into, "w"), indent=1)
+    else:
+        json.dump(rec, sys.stdout, indent=1)
 
 
 if __name__ == "__main__":
