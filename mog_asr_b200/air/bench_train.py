@@ -1,6 +1,7 @@
 """AIR-ASR training-step throughput (BASELINE configs 2-4) on synthetic canvases: images/sec."""
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -73,7 +74,18 @@ def run(name, device, steps=20, warmup=5, process_group=None, always_max_steps=F
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=process_group)
         ms = float(t.item())
-    return dict(config=name, images_per_sec=gbatch / (ms * 1e-3), ms_per_step=ms, global_batch=gbatch,
+    kernels_per_step = None
+    try:   # one profiled step: how many kernels the step is (the chain's length bounds strong scaling)
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_fn(batches[0])
+            torch.cuda.synchronize(device)
+        kernels_per_step = sum(1 for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
+                               and not e.name.lower().startswith(("memcpy", "memset")))
+    except Exception:
+        pass
+    return dict(config=name, images_per_sec=gbatch / (ms * 1e-3), ms_per_step=ms, global_batch=gbatch, kernels_per_step=kernels_per_step,
+                graph_branches=(os.environ.get("MOG_AIR_STREAMS", "1") != "0") if graph else False,
                 per_rank_batch=local, n_gpus=world, mean_loop_steps=T / steps, grad_floats=tr.num_gradient_floats(),
                 mode=("CUDA graph, fixed max_steps" if graph else "eager, fixed max_steps") if always_max_steps
                 else "eager, reference loop condition (host-checked any)")

@@ -16,7 +16,9 @@ Random draws (TF's ``random_normal`` / ``random_uniform`` streams cannot be repr
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Optional, Sequence
 
@@ -396,6 +398,22 @@ class AIRModel(nn.Module):
                 m.fuse = bool(getattr(self.ops, "fused_heads", False))
         self._vae_pair = _GaussPair(self.vae_rec_mean, self.vae_rec_logvar)
 
+    # ---- parallel branches of the captured step -------------------------------------------------------------------
+    # Inside a CUDA-graph capture independent chains of small kernels are recorded on side streams that fork from and
+    # rejoin the capture stream: they become parallel branches of the graph (the step is a dependent chain of ~650 small
+    # kernels; what bounds it at 512 images per GPU is the chain's length, not the work).  Autograd runs every node's
+    # backward on the stream of its forward, so the backward pass forks the same way.  Outside a capture (eager mode) the
+    # code runs on one stream: the caching allocator's cross-stream lifetime rules are not worth it there.
+    def _branch_streams(self, device, n, what="gen"):
+        mode = os.environ.get("MOG_AIR_STREAMS", "1")           # "0" off, "1" on, "gen" / "flush": one of the two uses only (experiments)
+        if not (device.type == "cuda" and mode in ("1", what) and torch.cuda.is_current_stream_capturing()):
+            return None
+        pool = self.__dict__.setdefault("_side_streams", {})
+        key = (device.index, n)
+        if key not in pool:
+            pool[key] = [torch.cuda.Stream(device) for _ in range(n)]
+        return pool[key]
+
     # ---- deferred weight gradients (see _DeferredAffine) ------------------------------------------------------
     def set_deferred_weight_grads(self, on: bool):
         for m in self.modules():
@@ -408,12 +426,39 @@ class AIRModel(nn.Module):
         self._vae_pair.reset()
 
     def flush_weight_grads(self):
+        jobs = []
         for m in self.modules():
             if isinstance(m, _StepAffine):
-                m.flush_grads()
+                jobs.append(m.flush_grads)
             if isinstance(m, _MeanVar):
-                m.flush_head()
-        self._vae_pair.flush()
+                jobs.append(m.flush_head)
+        jobs.append(self._vae_pair.flush)
+        dev = next(self.parameters()).device
+        side = self._branch_streams(dev, 3, "flush")
+        if side is None:
+            for j in jobs:
+                j()
+            return
+        # every flush writes its own layer's .grad: independent GEMMs, dealt out over the capture stream and three branches.
+        # The stashed rows were allocated on other streams than the one that reads them here: they are kept alive until the
+        # branches have rejoined, so that the allocator cannot hand their memory to a kernel that is not ordered after the read.
+        keep = []
+        for m in self.modules():
+            if isinstance(m, _StepAffine):
+                keep.extend(m._stash)
+            if isinstance(m, _MeanVar):
+                keep.extend(m._head_stash)
+        keep.extend(self._vae_pair.stash)
+        main = torch.cuda.current_stream(dev)
+        for st in side:
+            st.wait_stream(main)
+        lanes = [main] + side
+        for k, j in enumerate(jobs):
+            with torch.cuda.stream(lanes[k % len(lanes)]):
+                j()
+        for st in side:
+            main.wait_stream(st)
+        del keep
 
     # ---- pieces -------------------------------------------------------------------------------------------
     def _encode(self, window, eps):
@@ -600,19 +645,26 @@ class AIRModel(nn.Module):
             prev_latent, prev_ss = v_latent, torch.cat([shift_latent, scale_latent], -1)
 
         # ---- generative LSTM: input half for all steps at once, then its own chain ---------------------------
-        gen_static, gen_w = self.gen_cell.static_part(torch.cat(per["prev"], 0))
-        gen_static = gen_static.reshape(T, B, 4 * H).unbind(0)   # (unbind, not [step]: one stack in the backward pass
-        gen_state, gen_outs, none = (z(B, H), z(B, H)), [], z(B, 0)  #  instead of T zero-filled scatters that are then added)
-        for step in range(T):
-            g_out, gen_state = self.gen_cell(none, gen_state, static_gates=gen_static[step], static_width=gen_w, pointwise=lstm_pw)
-            gen_outs.append(g_out)
-        g_sh_mean, g_sh_lv = self.gen_shift(torch.cat(gen_outs, 0))                                            # :472-481
-        if cfg.fix_steps is not None:                                                                        # :604-608
-            prior_lo = torch.full((T, B), -100.0, device=dev, dtype=dt)
-            prior_lo[:cfg.fix_steps] = 100.0
-        else:
-            gen_prev = torch.cat([z(B, H)] + gen_outs[:-1], 0)
-            prior_lo = self.z_prior(self.z_prior_h(gen_prev, "relu")).reshape(T, B)                    # :609-615
+        # (a chain of its own: under graph capture it is a parallel branch beside the z_pres heads, the decoder, the
+        #  Concrete scan and the canvas writes below; it is needed again only by the KL terms of the epilogue)
+        side = self._branch_streams(dev, 1)
+        main = torch.cuda.current_stream(dev) if side is not None else None
+        if side is not None:
+            side[0].wait_stream(main)
+        with (torch.cuda.stream(side[0]) if side is not None else contextlib.nullcontext()):
+            gen_static, gen_w = self.gen_cell.static_part(torch.cat(per["prev"], 0))
+            gen_static = gen_static.reshape(T, B, 4 * H).unbind(0)   # (unbind, not [step]: one stack in the backward pass
+            gen_state, gen_outs, none = (z(B, H), z(B, H)), [], z(B, 0)  #  instead of T zero-filled scatters that are then added)
+            for step in range(T):
+                g_out, gen_state = self.gen_cell(none, gen_state, static_gates=gen_static[step], static_width=gen_w, pointwise=lstm_pw)
+                gen_outs.append(g_out)
+            g_sh_mean, g_sh_lv = self.gen_shift(torch.cat(gen_outs, 0))                                            # :472-481
+            if cfg.fix_steps is not None:                                                                        # :604-608
+                prior_lo = torch.full((T, B), -100.0, device=dev, dtype=dt)
+                prior_lo[:cfg.fix_steps] = 100.0
+            else:
+                gen_prev = torch.cat([z(B, H)] + gen_outs[:-1], 0)
+                prior_lo = self.z_prior(self.z_prior_h(gen_prev, "relu")).reshape(T, B)                    # :609-615
         post_lo = self.z_post(self.z_post_h(torch.cat(per["out"], 0), "relu")).reshape(T, B)            # :620-623
 
         # ---- VAE decoder for all steps (vae.py:34-41) ----------------------------------------------------------
@@ -628,6 +680,8 @@ class AIRModel(nn.Module):
             canvas = self.ops.write_composite(canvas, recon[step], per["theta_w"][step], z_pres, stop_sum, thr)
             y_pre_l.append(y_pre); act_prev_l.append(active_prev); act_l.append(active)
 
+        if side is not None:
+            main.wait_stream(side[0])          # the generative branch rejoins before the KL terms
         st = lambda k: torch.stack(per[k], 0)
         H_ = dict(y_pre=torch.stack(y_pre_l, 0), prior_lo=prior_lo, post_lo=post_lo, active_prev=torch.stack(act_prev_l, 0),
                   active=torch.stack(act_l, 0), sc_mean=st("sc_mean"), sc_lv=st("sc_lv"), sh_mean=st("sh_mean"), sh_lv=st("sh_lv"),

@@ -152,11 +152,13 @@ class Trainer:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = self.step(self.static_images, noise=noise)
+        self.t = t_host          # (tracing the step bumped the host-side counter; nothing ran)
         return self
 
     def step_graph(self, images):
         self.static_images.copy_(images, non_blocking=True)
         self.graph.replay()
+        self.t += 1
         return self.static_out
 
     def step(self, images, noise=None):

@@ -306,6 +306,34 @@ def test_loop_form_gradients_with_the_fused_kernels(cuda_device, always_max, dn)
 
 
 @pytest.mark.gpu
+def test_graph_step_with_parallel_branches_equals_single_stream_graph(cuda_device, monkeypatch):
+    """The captured training step records the generative chain and the weight-gradient flushes as parallel branches of
+    the CUDA graph (side streams that fork from and rejoin the capture stream).  Same seeds, same batches: after three
+    replays the parameters must equal those of the single-stream capture (up to the atomics of the head kernels), and
+    capturing must leave the training state untouched (the warm-up steps are rolled back)."""
+    cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0, always_max_steps=True)
+    B = 32
+    images, _ = make_images(B, 50, seed=12)
+    images = images.to(cuda_device)
+    finals = []
+    for streams in ("1", "0"):
+        monkeypatch.setenv("MOG_AIR_STREAMS", streams)
+        tr = Trainer(cfg, cuda_device, seed=21)
+        before = [p.detach().clone() for p in tr.params]
+        tr.capture(B)
+        assert all(torch.equal(a, b) for a, b in zip(before, tr.params)) and tr.t == 0 and float(tr.t_dev) == 0.0
+        torch.cuda.manual_seed(777)                      # identical noise streams for both captures
+        for _ in range(3):
+            out = tr.step_graph(images)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out["loss"]).all()
+        finals.append([p.detach().clone() for p in tr.params])
+    for a, b in zip(*finals):
+        # Adam moves every weight by ~lr per step; identical gradients up to atomic order leave the updates within a few % of lr
+        assert float((a - b).abs().max()) <= 3e-5, float((a - b).abs().max())
+
+
+@pytest.mark.gpu
 def test_one_step_changes_parameters_like_the_oracle_step(cuda_device):
     """After one full step (clip + TF-style Adam) both implementations hold the same parameters."""
     cfg = config_from_flags("mnist", "13", gm=100.0, gne=10.0, always_max_steps=True)
