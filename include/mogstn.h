@@ -21,6 +21,12 @@
  *     if a launch failed.  Nothing is thrown across the ABI.  mog_last_error_string() describes the
  *     last failure on the calling thread.
  *   - There is no CPU fallback anywhere in this library.
+ *   - Non-finite theta (e.g. 1/s = inf when a sigmoid scale underflows to 0, air_number_bbox_location.py:570-578) is
+ *     undefined in the reference (int32(floor(NaN)) is platform-defined).  Here a NaN or infinite source coordinate never
+ *     indexes out of bounds: the row / column counts as out of range, the forward writes what out-of-range pixels get
+ *     (exactly +0 for rows; NaN propagates through the weights of a column) and the backward contributes nothing for it.
+ *     The reference would carry NaN into the loss and zero it only at the gradient level (:1105-1108); a caller that
+ *     wants that behaviour must test theta for finiteness itself.
  */
 #ifndef MOGSTN_H_
 #define MOGSTN_H_

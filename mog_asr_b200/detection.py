@@ -24,6 +24,11 @@ def detection_metrics(gt_pos, gt_size, gt_num, inf_shifts, inf_scales, inf_num, 
     G = int(gt_pos.shape[1])
     if G > MAX_BOXES or T > MAX_BOXES:
         raise ValueError(f"at most {MAX_BOXES} ground-truth and {MAX_BOXES} inferred boxes per image (got {G}, {T})")
+    for t, n in ((gt_pos, "gt_pos"), (gt_size, "gt_size")):
+        # the kernel takes integer boxes (the reference's ground truth is integer pixels, multi_mnist.py:200-215); silently
+        # truncating a fractional box would change the IoUs, so it is refused
+        if t.is_floating_point() and bool((t != torch.floor(t)).any()):
+            raise ValueError(f"{n} must hold integer pixel coordinates (got non-integral values)")
     i32 = lambda t: t.to(device=dev, dtype=torch.int32).contiguous()
     gt_pos, gt_size, gt_num, inf_num = i32(gt_pos).reshape(B, G, 2), i32(gt_size).reshape(B, G, 2), i32(gt_num).reshape(B), i32(inf_num).reshape(B)
     shifts = inf_shifts.to(torch.float64).contiguous().reshape(B, T, 2)

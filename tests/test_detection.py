@@ -77,3 +77,18 @@ def test_cuda_rejects_too_many_boxes(cuda_device):
     z = lambda *s: torch.zeros(*s, device=dev)
     with pytest.raises(ValueError):
         detection.detection_metrics(z(2, 9, 2), z(2, 9, 2), z(2), z(2, 3, 2), z(2, 3), z(2), 50)
+
+
+@pytest.mark.gpu
+def test_non_integral_ground_truth_is_refused(cuda_device):
+    """float ground-truth boxes with fractional coordinates would be truncated by the int32 kernel interface: refused."""
+    import torch
+    from mog_asr_b200 import detection
+    pos = torch.tensor([[[3.5, 4.0]]], device=cuda_device)
+    size = torch.tensor([[[10.0, 10.0]]], device=cuda_device)
+    num = torch.tensor([1], device=cuda_device)
+    sh = torch.zeros((1, 1, 2), device=cuda_device, dtype=torch.float64)
+    sc = torch.full((1, 1), 0.3, device=cuda_device, dtype=torch.float64)
+    with pytest.raises(ValueError):
+        detection.detection_metrics(pos, size, num, sh, sc, num, 50)
+    detection.detection_metrics(torch.floor(pos), size, num, sh, sc, num, 50)    # integral floats are fine
