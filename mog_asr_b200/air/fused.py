@@ -26,12 +26,15 @@ class _GaussSample(torch.autograd.Function):
                                                       act, _stream(mean)), "mog_air_gauss_sample_forward")
         ctx.save_for_backward(logvar, eps, squashed)
         ctx.act = act
+        ctx.set_materialize_grads(False)     # an unused output's gradient arrives as None, not as a zero-filled tensor (one fill kernel each)
         return (latent, squashed) if act else (latent, latent.new_empty(0))
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_latent, g_squashed):
         logvar, eps, squashed = ctx.saved_tensors
+        if g_latent is None and (g_squashed is None or not ctx.act):
+            return None, None, None, None
         L = _lib.load()
         g_latent = g_latent.contiguous() if g_latent is not None else None
         g_squashed = g_squashed.contiguous() if (ctx.act and g_squashed is not None) else None
@@ -63,6 +66,7 @@ class _Thetas(torch.autograd.Function):
         with torch.cuda.device(shift.device):
             _lib.check(L.mog_air_thetas_forward(_p(shift), _p(scale), _p(th_r), _p(th_w), B, _stream(shift)), "mog_air_thetas_forward")
         ctx.save_for_backward(shift, scale)
+        ctx.set_materialize_grads(False)
         return th_r, th_w
 
     @staticmethod
@@ -72,6 +76,10 @@ class _Thetas(torch.autograd.Function):
         L = _lib.load()
         B = shift.shape[0]
         d_shift, d_scale = torch.empty_like(shift), torch.empty_like(scale)
+        if g_r is None and g_w is None:
+            return None, None
+        g_r = torch.zeros((B, 6), dtype=torch.float32, device=shift.device) if g_r is None else g_r
+        g_w = torch.zeros((B, 6), dtype=torch.float32, device=shift.device) if g_w is None else g_w
         with torch.cuda.device(shift.device):
             _lib.check(L.mog_air_thetas_backward(_p(shift), _p(scale), _p(g_r.contiguous()), _p(g_w.contiguous()), _p(d_shift),
                                                  _p(d_scale), B, _stream(shift)), "mog_air_thetas_backward")
@@ -100,12 +108,15 @@ class _ZPres(torch.autograd.Function):
         ctx.save_for_backward(z)
         ctx.temperature = float(temperature)
         ctx.mark_non_differentiable(s1, ap, ac)
+        ctx.set_materialize_grads(False)
         return y, z, s1, ap, ac
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_y, g_z, _gs, _gap, _gac):
         (z,) = ctx.saved_tensors
+        if g_y is None and g_z is None:
+            return None, None, None, None, None
         L = _lib.load()
         d_lo = torch.empty_like(z)
         g_y = g_y.contiguous() if g_y is not None else None
@@ -133,12 +144,15 @@ class _LstmPointwise(torch.autograd.Function):
             _lib.check(L.mog_air_lstm_pointwise_forward(_p(gates), _p(gates2), _p(c_prev), _p(c_new), _p(h_new), B, H, _stream(gates)),
                        "mog_air_lstm_pointwise_forward")
         ctx.save_for_backward(gates, c_prev, c_new, gates2)
+        ctx.set_materialize_grads(False)
         return c_new, h_new
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_c, g_h):
         gates, c_prev, c_new, gates2 = ctx.saved_tensors
+        if g_c is None and g_h is None:
+            return None, None, None
         L = _lib.load()
         B, H = c_prev.shape
         g_c = g_c.contiguous() if g_c is not None else None
