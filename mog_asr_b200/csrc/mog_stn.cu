@@ -50,6 +50,9 @@ int sm_count() {
 #ifndef MOG_BULK_ZERO
 #define MOG_BULK_ZERO 1   // large zero regions go to the bulk-copy engine (0: ordinary stores; A/B experiments)
 #endif
+#ifndef MOG_FILL_EVERY_DEFAULT
+#define MOG_FILL_EVERY_DEFAULT 0
+#endif
 #ifndef MOG_COOP_ZERO_MIN_FLOATS
 #define MOG_COOP_ZERO_MIN_FLOATS 8192   // dU images of >= 32 KB are zero-filled by the whole CTA
 #endif
@@ -130,10 +133,22 @@ static int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
+// MOG_FILL_EVERY = R: every R-th CTA of the large-output kernels only feeds the bulk-copy engine (0 / 1: every warp fills
+// its own image).  Default chosen by measurement (profiles/r02_kernel_experiments.md).
+static int fill_every_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOG_FILL_EVERY");
+        v = e ? atoi(e) : MOG_FILL_EVERY_DEFAULT;
+    }
+    return v;
+}
+
 template <bool COMPOSITE>
 static int launch_fwd(FwdArgs a, cudaStream_t st) {
     if (a.B == 0) return MOG_OK;
     a.bulk_zero = (!COMPOSITE && MOG_BULK_ZERO && (long long)a.g.N * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS) ? 1 : 0;
+    a.fill_every = a.bulk_zero ? fill_every_setting() : 0;
     const size_t smem = (size_t)kWarpsPerCta * (a.g.Ho + a.g.Wo) * sizeof(int4) + (a.bulk_zero ? kZeroBytes : 0);
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d too large for the per-warp tables", a.g.Ho, a.g.Wo);
     if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
@@ -318,6 +333,7 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.Bsrc == 0) return MOG_OK;
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
+    a.fill_every = a.coop_zero == 2 ? fill_every_setting() : 0;
     const BwdImpl impl = bwd_impl();
     if (impl == kBwdCta || impl == kBwdAuto) {
         static const int rd_on = env_flag("MOG_BWD_RD", 0);
