@@ -58,5 +58,5 @@ if len(rows) > 1:
         s = t["C4_global4096"]
         w = t.get("C4_weak_4096_per_gpu", s)
         dc = t.get("dp_check", {})
-        out.append(f"| {r['n_gpus']} | {r['value']/1e6:.2f} M | {r['value']/v1:.2f} | {r['e2e']['value']/1e6:.3f} M | {s['images_per_sec']/1e3:.0f} k ({s['ms_per_step']:.2f} ms/step; {s['images_per_sec']/t1['images_per_sec']:.2f}x) | {w['images_per_sec']/1e3:.0f} k ({w['ms_per_step']:.2f} ms/step; {w['images_per_sec']/t1['images_per_sec']:.2f}x) | {dc.get('max_rel_diff', '-') if dc else '-'} |")
+        out.append(f"| {r['n_gpus']} | {r['value']/1e6:.2f} M | {r['value']/v1:.2f} | {r['e2e']['value']/1e6:.3f} M | {s['images_per_sec']/1e3:.0f} k ({s['ms_per_step']:.2f} ms/step; {s['images_per_sec']/t1['images_per_sec']:.2f}x) | {w['images_per_sec']/1e3:.0f} k ({w['ms_per_step']:.2f} ms/step; {w['images_per_sec']/t1['images_per_sec']:.2f}x) | {('%.1e' % dc['max_rel_diff']) if dc and 'max_rel_diff' in dc else '-'} |")
 print("\n".join(out))
