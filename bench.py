@@ -13,8 +13,9 @@ theta_w), each forward + backward(dU + dtheta).  One bench "step" = those 8 AIR 
 = 16 * B glimpses.  Batch shards are independent, so N GPUs run N shards (weak scaling, no collective).
 
 `value`: glimpses/s with inputs resident in HBM (CUDA events, max over ranks).
-`e2e`  : the same 16*B glimpses through the host-buffer entry point mog_stn_fwd_bwd_host (pinned host
-         arrays in, host arrays out, copies inside the timed region).
+`e2e`  : the same 16*B glimpses through the host-buffer entry points (pinned host arrays in, host arrays out,
+         copies inside the timed region): mog_stn_batch_fwd_bwd_host for the reads, mog_stn_write_composite_host for
+         the writes (the AIR loop's data flow); `e2e.separate_write_canvases` = every write step's canvas on its own.
 `roofline`: algorithmic bytes (fwd 4(F+O)+24, bwd 4(O+F+S)+48 per glimpse, F = distinct
          source pixels addressed) of the dominant kernel / its mean duration, vs MEASURED_PEAKS.json.
 `cpu_baseline`: oracle C restatement (all host threads) on a bounded sample of the same workload.
@@ -323,39 +324,76 @@ class GpuWorkload:
         return out
 
 
-def e2e_measure(a, dev, steps, warmup):
+def e2e_measure(a, dev, steps, warmup, composite=True):
     """Same 16*B glimpses per step, host (pinned) arrays in and out through the host entry points.  Read direction: ONE
     mog_stn_batch_fwd_bwd_host call (the reference's batch_transformer form: the canvases cross the bus once for their 8
     thetas, dU -- summed over the 8 steps, what autodiff of 8 reads of one canvas yields -- comes back once).  Write
-    direction: 8 mog_stn_fwd_bwd_host calls (every step has its own window, gradient and output canvas)."""
+    direction, composite=True (the AIR loop's data flow, :592-600 + :718-727): ONE mog_stn_write_composite_host call -- 8
+    distinct windows per image written onto one canvas per image, the canvas gradient differentiated back to all 8 steps
+    (dW, dtheta, dz); composite=False: 8 mog_stn_fwd_bwd_host calls, every step with its own output canvas and gradient
+    (the device-resident leg's form; 8x the canvas traffic)."""
     import torch
     from mog_asr_b200 import synth
-    from mog_asr_b200.host_api import HostSampler
+    from mog_asr_b200.host_api import HostCompositeWriter, HostSampler
     B, cs, gs, T = a.e2e_batch, a.canvas, a.glimpse, AIR_STEPS
     pin = lambda *shape: torch.empty(shape, dtype=torch.float32).pin_memory()
-    U_h, W_h, g_r, g_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, T, gs, gs, 1), pin(B, cs, cs, 1)
     gdev = torch.Generator(device=dev).manual_seed(10)   # fill the host arrays from device-generated data (fast)
-    for t, normal in ((U_h, False), (W_h, False), (g_r, True), (g_w, True)):
-        tmp = (torch.randn if normal else torch.rand)(tuple(t.shape), device=dev, generator=gdev)
-        t.copy_(tmp)
-        del tmp
+
+    def filled(t, normal):
+        flat = t.view(-1)
+        for o in range(0, flat.numel(), 1 << 28):
+            n = min(1 << 28, flat.numel() - o)
+            flat[o:o + n].copy_((torch.randn if normal else torch.rand)((n,), device=dev, generator=gdev))
+        return t
+    U_h, g_r = filled(pin(B, cs, cs, 1), False), filled(pin(B, T, gs, gs, 1), True)
     gen = synth.sxy_prior_like if a.regime == "prior" else synth.sxy_full_cover
     th_r, th_w = [], []
     for t in range(T):
         s, x, y = gen(B, seed=100 + t)
         th_r.append(synth.theta_read(s, x, y))
-        th_w.append(torch.from_numpy(synth.theta_write(s, x, y)).pin_memory())
+        th_w.append(synth.theta_write(s, x, y))
     th_r = torch.from_numpy(np.ascontiguousarray(np.stack(th_r, 1))).pin_memory()          # [B, T, 6]
-    out_r, dU_r, out_w, dU_w = pin(B * T, gs, gs, 1), pin(B, cs, cs, 1), pin(B, cs, cs, 1), pin(B, gs, gs, 1)
-    dth_r, dth_w = pin(B, T, 6), pin(B, 6)
+    out_r, dU_r, dth_r = pin(B * T, gs, gs, 1), pin(B, cs, cs, 1), pin(B, T, 6)
     chunk = max(256, min(512, B // 8))
-    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(32, chunk // T), transforms=T)
-    wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=chunk)
+    rd = HostSampler(dev, (cs, cs), (gs, gs), 1, chunk=max(32, chunk // 4), transforms=T)   # measured: tools/e2e_probe.py
+    fl = 4
+    h2d = fl * (U_h.numel() + g_r.numel() + th_r.numel())
+    d2h = fl * (out_r.numel() + dU_r.numel() + dth_r.numel())
+    launches = 2 * (-(-B // rd.chunk))                                   # forward + backward per chunk
+    if composite:
+        W_h, g_c = filled(pin(T, B, gs, gs), False), filled(pin(B, cs, cs), True)
+        z_h = filled(pin(T, B), False)
+        th_wh = torch.from_numpy(np.ascontiguousarray(np.stack(th_w, 0))).pin_memory()     # [T, B, 6]
+        canvas, dW, dth_w, dz = pin(B, cs, cs), pin(T, B, gs, gs), pin(T, B, 6), pin(T, B)
+        wr = HostCompositeWriter(dev, (gs, gs), (cs, cs), steps=T, chunk=chunk, nstreams=4)
+
+        def write():
+            wr.fwd_bwd(W_h, th_wh, z_h, g_c, canvas=canvas, dW=dW, dtheta=dth_w, dz=dz)
+        h2d += fl * (W_h.numel() + th_wh.numel() + z_h.numel() + g_c.numel())
+        d2h += fl * (canvas.numel() + dW.numel() + dth_w.numel() + dz.numel())
+        launches += 2 * T * (-(-B // wr.chunk))
+        api = ("read: mog_stn_batch_fwd_bwd_host (canvases uploaded once for the 8 thetas, dU summed over them, downloaded once); "
+               "write: mog_stn_write_composite_host (8 distinct windows per image composited onto one canvas per image, the canvas "
+               "gradient differentiated back to the 8 windows / thetas / z_pres: the AIR loop's data flow); pinned host arrays "
+               "in/out, chunked over 3-4 streams")
+    else:
+        W_h, g_w = filled(pin(B, gs, gs, 1), False), filled(pin(B, cs, cs, 1), True)
+        th_wl = [torch.from_numpy(t).pin_memory() for t in th_w]
+        out_w, dU_w, dth_w = pin(B, cs, cs, 1), pin(B, gs, gs, 1), pin(B, 6)
+        wr = HostSampler(dev, (gs, gs), (cs, cs), 1, chunk=chunk)
+
+        def write():
+            for t in range(T):
+                wr.fwd_bwd(W_h, th_wl[t], g_w, out=out_w, dU=dU_w, dtheta=dth_w)
+        h2d += fl * T * (W_h.numel() + g_w.numel() + 6 * B)
+        d2h += fl * T * (out_w.numel() + dU_w.numel() + 6 * B)
+        launches += T * 2 * (-(-B // wr.chunk))
+        api = ("read: mog_stn_batch_fwd_bwd_host; write: 8 x mog_stn_fwd_bwd_host (every step its own 256x256 output canvas and "
+               "upstream gradient across the bus); pinned host arrays in/out, chunked over 3 streams")
 
     def step():
         rd.batch_fwd_bwd(U_h, th_r, g_r, out=out_r, dU=dU_r, dtheta=dth_r)
-        for t in range(T):
-            wr.fwd_bwd(W_h, th_w[t], g_w, out=out_w, dU=dU_w, dtheta=dth_w)
+        write()
 
     for _ in range(warmup):
         step()
@@ -365,11 +403,7 @@ def e2e_measure(a, dev, steps, warmup):
         step()
     torch.cuda.synchronize(dev)
     dt = (time.perf_counter() - t0) / steps
-    fl = 4
-    h2d = fl * (U_h.numel() + g_r.numel() + th_r.numel() + T * (W_h.numel() + g_w.numel() + 6 * B))
-    d2h = fl * (out_r.numel() + dU_r.numel() + dth_r.numel() + T * (out_w.numel() + dU_w.numel() + 6 * B))
-    launches = 2 * (-(-B // rd.chunk)) + T * 2 * (-(-B // wr.chunk))   # forward + backward per chunk and call
-    return dt, h2d, d2h, launches
+    return dt, h2d, d2h, launches, api
 
 
 def config1_section(dev, no_cpu):
@@ -722,14 +756,18 @@ def run_ours(a):
     if not a.no_e2e:
         e_steps = 2 if a.batch * a.canvas ** 2 > (1 << 28) else max(2, a.steps // 10)
         trace("e2e leg")
-        dt, h2d, d2h, e2e_launches = e2e_measure(a, dev, e_steps, 1)
+        dt, h2d, d2h, e2e_launches, api = e2e_measure(a, dev, max(e_steps, 3), 1)
         trace("e2e done")
         barrier()
         dt = max_over_ranks(dt)
         e2e = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt, unit=UNIT, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3, steps=e_steps, batch_per_gpu=a.e2e_batch,
-                   api="read: mog_stn_batch_fwd_bwd_host (canvases uploaded once for the 8 thetas, dU summed over them, downloaded "
-                       "once); write: 8 x mog_stn_fwd_bwd_host; pinned host arrays in/out, chunked over 3 streams")
+                   d2h_bytes_per_step=int(d2h), ms_per_step=dt * 1e3, steps=max(e_steps, 3), batch_per_gpu=a.e2e_batch, api=api)
+        # the same glimpses with every write step's 256x256 canvas and gradient crossing the bus separately (round-1/2 form)
+        dt2, h2d2, d2h2, _, api2 = e2e_measure(a, dev, 1, 1, composite=False)
+        barrier()
+        dt2 = max_over_ranks(dt2)
+        e2e["separate_write_canvases"] = dict(value=a.e2e_batch * 2 * AIR_STEPS * world / dt2, unit=UNIT, h2d_bytes_per_step=int(h2d2),
+                                              d2h_bytes_per_step=int(d2h2), ms_per_step=dt2 * 1e3, steps=1, api=api2)
     tc2 = time.perf_counter()
     sampler.stop_flag = True
     clocks = sampler.summary(tc0, tc2 if e2e else tc1)
@@ -743,7 +781,9 @@ def run_ours(a):
                            frac=abytes[k] / (kern_ms[k] * 1e-3) / 1e9 / peak) for k in wl.kinds}
         nxc = lambda w: 1 if w <= 32 else (2 if w <= 64 else 4)
         sym = dict(read_fwd="stn_fwd_warp_kernel<false>", write_fwd="stn_fwd_warp_kernel<false>",
-                   read_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.canvas)}>", write_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.glimpse)}>")
+                   read_bwd=f"stn_bwd_warp_kernel<false,{nxc(a.canvas)}>",
+                   write_bwd=("stn_bwd_cta_kernel<false,8,%d>" % (1 if a.glimpse ** 2 > 1024 else 2)) if (a.canvas >= 192 and a.glimpse <= 64)
+                   else f"stn_bwd_warp_kernel<false,{nxc(a.glimpse)}>")
         # physical DRAM bytes per launch of ALL four kernels, from the ncu capture committed with this bench line
         # (tools/traffic_capture.py: dram__bytes_read.sum + dram__bytes_write.sum, same cell, same batch)
         traffic, traffic_src, tj = None, None, None

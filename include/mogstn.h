@@ -108,6 +108,19 @@ MOG_API int mog_stn_write_composite_backward(const float* U, const float* theta,
                                      float* dtheta, float* dz, int64_t B, int Hw, int Ww, int Hc, int Wc,
                                      void* stream);
 
+/* The write call site of the AIR loop on HOST buffers (air_number_bbox_location.py:592-600 and :718-727): T windows per
+ * image are written onto ONE canvas per image, canvas[b] = sum_t z[t][b] * sample(W[t][b]; theta[t][b]) (accumulated in
+ * step order, exactly as T calls of mog_stn_write_composite_forward on a zero canvas), and gcanvas_h = d loss / d canvas
+ * is differentiated back to every step's window, theta and z_pres.  Step-major arrays (the model's stacks): W_h
+ * [T][B][Hw][Ww], thetas_h [T][B][6], z_h [T][B]; canvas_h / gcanvas_h [B][Hc][Wc]; dW_h, dtheta_h, dz_h (each nullable)
+ * like W_h, thetas_h, z_h.  gcanvas_h may be NULL when no gradient is requested.  The canvas crosses the bus once per
+ * image instead of once per glimpse.  chunk counts images; waits for its streams before returning. */
+MOG_API int mog_stn_write_composite_host(const float* W_h, const float* thetas_h, const float* z_h, const float* gcanvas_h,
+                                 float* canvas_h, float* dW_h, float* dtheta_h, float* dz_h, int64_t B, int T, int Hw,
+                                 int Ww, int Hc, int Wc, int64_t chunk, void* workspace_d, size_t workspace_bytes,
+                                 void* const* streams, int nstreams);
+MOG_API size_t mog_stn_write_composite_host_workspace_bytes(int64_t chunk, int T, int Hw, int Ww, int Hc, int Wc, int nstreams);
+
 /* ---- ASR regularisers (one fused per-image kernel) ------------------------------------------------ */
 #define MOG_ASR_MAX_STEPS 16
 #define MOG_ASR_MAX_COUNTS 8

@@ -539,3 +539,101 @@ extern "C" int mog_stn_fwd_bwd_host(const float* U_h, const float* theta_h, cons
     return mog_stn_batch_fwd_bwd_host(U_h, theta_h, gout_h, out_h, dU_h, dtheta_h, B, 1, Hs, Ws, C, Ho, Wo, chunk, workspace_d,
                                       workspace_bytes, streams, nstreams);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// The write call site of the AIR loop on host buffers (air_number_bbox_location.py:592-600 + :718-727): T windows per image
+// are written onto ONE canvas per image,  canvas[b] = sum_t z[t][b] * sample(W[t][b]; theta[t][b]),  and the gradient of
+// the canvas reaches every step's window, theta and z_pres.  Step-major layout ([T][B]...: the model's stacks), so a chunk
+// of images is T contiguous pieces per array.  The canvas crosses PCIe once per image instead of once per glimpse.
+// ---------------------------------------------------------------------------------------------------
+struct CompositeChunkLayout {
+    size_t W, theta, z, canvas, gcanvas, dW, dtheta, dz, total;
+};
+
+static CompositeChunkLayout composite_chunk_layout(int64_t chunk, int T, int Hw, int Ww, int Hc, int Wc) {
+    CompositeChunkLayout l;
+    size_t o = 0;
+    l.W = o;       o += align256((size_t)chunk * T * Hw * Ww * sizeof(float));
+    l.theta = o;   o += align256((size_t)chunk * T * 6 * sizeof(float));
+    l.z = o;       o += align256((size_t)chunk * T * sizeof(float));
+    l.canvas = o;  o += align256((size_t)chunk * Hc * Wc * sizeof(float));
+    l.gcanvas = o; o += align256((size_t)chunk * Hc * Wc * sizeof(float));
+    l.dW = o;      o += align256((size_t)chunk * T * Hw * Ww * sizeof(float));
+    l.dtheta = o;  o += align256((size_t)chunk * T * 6 * sizeof(float));
+    l.dz = o;      o += align256((size_t)chunk * T * sizeof(float));
+    l.total = o;
+    return l;
+}
+
+extern "C" size_t mog_stn_write_composite_host_workspace_bytes(int64_t chunk, int T, int Hw, int Ww, int Hc, int Wc, int nstreams) {
+    if (chunk <= 0 || T <= 0 || Hw <= 0 || Ww <= 0 || Hc <= 0 || Wc <= 0 || nstreams <= 0) return 0;
+    return composite_chunk_layout(chunk, T, Hw, Ww, Hc, Wc).total * (size_t)nstreams;
+}
+
+extern "C" int mog_stn_write_composite_host(const float* W_h, const float* thetas_h, const float* z_h, const float* gcanvas_h,
+                                            float* canvas_h, float* dW_h, float* dtheta_h, float* dz_h, int64_t B, int T, int Hw,
+                                            int Ww, int Hc, int Wc, int64_t chunk, void* workspace_d, size_t workspace_bytes,
+                                            void* const* streams, int nstreams) {
+    MOG_REQUIRE(T >= 1 && T <= 4096, MOG_ERR_DIM, "write_composite_host: T=%d", T);
+    if (int rc = check_dims(B, Hw, Ww, 1, Hc, Wc, 1)) return rc;
+    MOG_REQUIRE(chunk > 0 && nstreams > 0 && nstreams <= 16, MOG_ERR_DIM, "write_composite_host: chunk=%lld nstreams=%d", (long long)chunk, nstreams);
+    if (B == 0) return MOG_OK;
+    MOG_REQUIRE(W_h && thetas_h && z_h && canvas_h && workspace_d && streams, MOG_ERR_NULL, "write_composite_host: NULL pointer");
+    const bool bwd = dW_h || dtheta_h || dz_h;
+    MOG_REQUIRE(gcanvas_h || !bwd, MOG_ERR_NULL, "write_composite_host: gradients requested without gcanvas");
+    const CompositeChunkLayout l = composite_chunk_layout(chunk, T, Hw, Ww, Hc, Wc);
+    MOG_REQUIRE(workspace_bytes >= l.total * (size_t)nstreams, MOG_ERR_DIM, "write_composite_host: workspace %zu B < required %zu B",
+                workspace_bytes, l.total * (size_t)nstreams);
+    const size_t imW = (size_t)Hw * Ww, imC = (size_t)Hc * Wc;
+    const Geo g = make_geo(Hw, Ww, 1, Hc, Wc);
+    int k = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++k) {
+        const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        cudaStream_t st = (cudaStream_t)streams[k % nstreams];
+        char* base = (char*)workspace_d + l.total * (size_t)(k % nstreams);
+        float* dWin = (float*)(base + l.W);
+        float* dth = (float*)(base + l.theta);
+        float* dzp = (float*)(base + l.z);
+        float* dcv = (float*)(base + l.canvas);
+        float* dgc = (float*)(base + l.gcanvas);
+        float* ddW = (float*)(base + l.dW);
+        float* ddth = (float*)(base + l.dtheta);
+        float* ddz = (float*)(base + l.dz);
+        // device chunk layout is step-major too: step t of the chunk at offset t * nb
+        for (int t = 0; t < T; ++t) {
+            const size_t h = (size_t)t * B + b0, d = (size_t)t * nb;
+            MOG_CUDA_TRY(cudaMemcpyAsync(dWin + d * imW, W_h + h * imW, nb * imW * sizeof(float), cudaMemcpyHostToDevice, st));
+            MOG_CUDA_TRY(cudaMemcpyAsync(dth + d * 6, thetas_h + h * 6, nb * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+            MOG_CUDA_TRY(cudaMemcpyAsync(dzp + d, z_h + h, nb * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        if (bwd) MOG_CUDA_TRY(cudaMemcpyAsync(dgc, gcanvas_h + b0 * imC, nb * imC * sizeof(float), cudaMemcpyHostToDevice, st));
+        MOG_CUDA_TRY(cudaMemsetAsync(dcv, 0, nb * imC * sizeof(float), st));
+        for (int t = 0; t < T; ++t) {   // canvas += z_t * sample(W_t; theta_t), in place (only in-range rows are touched)
+            const size_t d = (size_t)t * nb;
+            FwdArgs fa{};
+            fa.U = dWin + d * imW; fa.theta = dth + d * 6; fa.out = dcv; fa.z_pres = dzp + d; fa.stop_sum = nullptr;
+            fa.canvas_in = dcv; fa.threshold = 0.0f; fa.B = nb; fa.u_div = 1; fa.g = g;
+            if (int rc = launch_fwd<true>(fa, st)) return rc;
+        }
+        MOG_CUDA_TRY(cudaMemcpyAsync(canvas_h + b0 * imC, dcv, nb * imC * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (bwd) {
+            for (int t = 0; t < T; ++t) {
+                const size_t d = (size_t)t * nb;
+                BwdArgs ba{};
+                ba.U = dWin + d * imW; ba.theta = dth + d * 6; ba.gout = dgc; ba.z_pres = dzp + d; ba.stop_sum = nullptr;
+                ba.dU = dW_h ? ddW + d * imW : nullptr; ba.dtheta = dtheta_h ? ddth + d * 6 : nullptr; ba.dz = dz_h ? ddz + d : nullptr;
+                ba.threshold = 0.0f; ba.Bsrc = nb; ba.u_div = 1; ba.g = g;
+                if (int rc = launch_bwd<true>(ba, st)) return rc;
+            }
+            for (int t = 0; t < T; ++t) {
+                const size_t h = (size_t)t * B + b0, d = (size_t)t * nb;
+                if (dW_h) MOG_CUDA_TRY(cudaMemcpyAsync(dW_h + h * imW, ddW + d * imW, nb * imW * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (dtheta_h) MOG_CUDA_TRY(cudaMemcpyAsync(dtheta_h + h * 6, ddth + d * 6, nb * 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                if (dz_h) MOG_CUDA_TRY(cudaMemcpyAsync(dz_h + h, ddz + d, nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    const int used = k < nstreams ? k : nstreams;
+    for (int i = 0; i < used; ++i) MOG_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)streams[i]));
+    return MOG_OK;
+}

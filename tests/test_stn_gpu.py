@@ -301,6 +301,39 @@ def test_batch_host_entry_point_matches_batch_transformer(cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ws,cs,B,T,chunk", [(28, 50, 150, 3, 64), (64, 256, 70, 4, 32)])
+def test_write_composite_host_entry_point_matches_the_device_loop(cuda_device, ws, cs, B, T, chunk):
+    """mog_stn_write_composite_host: T windows per image composited onto one canvas per image from step-major host arrays,
+    canvas gradient differentiated back to every step -- same bits as T device calls of write_composite + autograd
+    (reference loop :592-600, :718-727), ragged last chunk, forward-only and partial-gradient forms; and the first step
+    against the numpy oracle."""
+    from mog_asr_b200.host_api import HostCompositeWriter
+    rng = np.random.default_rng(ws + cs)
+    W = torch.from_numpy(rng.random((T, B, ws, ws), dtype=np.float32)).pin_memory()
+    s, x, y = synth.sxy_prior_like(T * B, seed=12)
+    th = torch.from_numpy(synth.theta_write(s, x, y).reshape(T, B, 6)).pin_memory()
+    z = torch.from_numpy(rng.random((T, B), dtype=np.float32)).pin_memory()
+    g = torch.from_numpy(rng.standard_normal((B, cs, cs), dtype=np.float32)).pin_memory()
+    hw = HostCompositeWriter(cuda_device, (ws, ws), (cs, cs), steps=T, chunk=chunk, nstreams=3)
+    canvas, dW, dth, dz = hw.fwd_bwd(W, th, z, g)
+    Wd, td, zd = (t.to(cuda_device).requires_grad_(True) for t in (W, th, z))
+    c = torch.zeros((B, cs, cs), device=cuda_device)
+    for t in range(T):
+        c = M.write_composite(c, Wd[t], td[t], zd[t])
+    c.backward(g.to(cuda_device))
+    assert torch.equal(canvas, c.detach().cpu())
+    assert torch.equal(dW, Wd.grad.cpu()) and torch.equal(dth, td.grad.cpu()) and torch.equal(dz, zd.grad.cpu())
+    c2, dW2, dth2, dz2 = hw.fwd_bwd(W, th, z)                      # forward only
+    assert dW2 is None and dth2 is None and dz2 is None and torch.equal(c2, canvas)
+    c3, dW3, dth3, dz3 = hw.fwd_bwd(W, th, z, g, need_dW=False)
+    assert dW3 is None and torch.equal(dth3, dth) and torch.equal(dz3, dz)
+    hw1 = HostCompositeWriter(cuda_device, (ws, ws), (cs, cs), steps=1, chunk=chunk, nstreams=2)
+    c1 = hw1.fwd_bwd(W[:1].contiguous(), th[:1].contiguous(), z[:1].contiguous())[0].numpy()
+    ref = R.transformer(W[0].numpy()[..., None], th[0].numpy(), (cs, cs))[..., 0] * z[0].numpy()[:, None, None]
+    np.testing.assert_array_equal(c1, ref + np.float32(0.0))
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("src,dst", [((131, 127), (33, 29)), ((33, 29), (131, 127)), ((256, 256), (64, 64)), ((64, 64), (256, 256)),
                                      ((90, 93), (90, 93))])
 def test_large_images_every_element_written(cuda_device, src, dst):
