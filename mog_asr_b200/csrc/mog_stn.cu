@@ -17,6 +17,7 @@
 #include "mog_stn_bwd.cuh"
 #include "mog_stn_bwd_tma.cuh"
 #include "mog_stn_bwd_cta.cuh"
+#include "mog_stn_bwd_col.cuh"
 #include "mog_stn_bwd_rd.cuh"
 
 #include <cudaTypedefs.h>
@@ -292,6 +293,32 @@ static int launch_bwd_cta(const BwdArgs& a, cudaStream_t st) {
     return nbuf == 2 ? launch_bwd_cta_shape<COMPOSITE, 8, 2>(a, st) : launch_bwd_cta_shape<COMPOSITE, 8, 1>(a, st);
 }
 
+// Source-column form (mog_stn_bwd_col.cuh): one warp per image, lanes along the source columns; for outputs at least about
+// as wide as the source (the write direction).
+static bool bwd_col_eligible(const BwdArgs& a) {
+    const Geo& g = a.g;
+    return g.C == 1 && a.u_div == 1 && g.Ws <= kColMaxWs && g.Wo < 65536 &&
+           (size_t)bwd_col_layout(g).total * kWarpsPerCta <= (size_t)kMaxSmemBytes;
+}
+
+template <bool COMPOSITE, int NCOL>
+static int launch_bwd_col_n(const BwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)bwd_col_layout(a.g).total * kWarpsPerCta;
+    if (int rc = set_smem(stn_bwd_col_kernel<COMPOSITE, NCOL>, smem)) return rc;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_bwd_col_kernel<COMPOSITE, NCOL>, kWarpsPerCta * 32, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
+    stn_bwd_col_kernel<COMPOSITE, NCOL><<<grid_for(ctas, per_sm), kWarpsPerCta * 32, smem, st>>>(a);
+    MOG_CUDA_LAUNCH_CHECK("stn_bwd_col_kernel");
+    return MOG_OK;
+}
+
+template <bool COMPOSITE>
+static int launch_bwd_col(const BwdArgs& a, cudaStream_t st) {
+    return a.g.Ws <= 32 ? launch_bwd_col_n<COMPOSITE, 1>(a, st) : launch_bwd_col_n<COMPOSITE, 2>(a, st);
+}
+
 // Read direction with dU (mog_stn_bwd_rd.cuh): large source, glimpse-sized output, fill and arithmetic in different warps.
 static bool bwd_rd_eligible(const BwdArgs& a) {
     const Geo& g = a.g;
@@ -314,7 +341,7 @@ static int launch_bwd_rd(const BwdArgs& a, cudaStream_t st) {
 // tie at 128, slower below), the warp-per-image streaming kernel everywhere else.  "stream" / "cta" force one of the two
 // (cta falls back where ineligible); "group" (grouped gather form, register loads) and "tma" (grouped form, source and
 // gradient tiles staged by TMA) are the two experimental formulations kept for comparison (slower, see profiles/).
-enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2, kBwdCta = 3, kBwdAuto = 4 };
+enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2, kBwdCta = 3, kBwdAuto = 4, kBwdCol = 5 };
 static BwdImpl bwd_impl() {
     static int v = -1;
     if (v < 0) {
@@ -324,6 +351,7 @@ static BwdImpl bwd_impl() {
         if (e && strcmp(e, "group") == 0) v = kBwdGroup;
         if (e && strcmp(e, "tma") == 0) v = kBwdTma;
         if (e && strcmp(e, "cta") == 0) v = kBwdCta;
+        if (e && strcmp(e, "col") == 0) v = kBwdCol;
     }
     return (BwdImpl)v;
 }
@@ -335,6 +363,7 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     a.fill_every = a.coop_zero == 2 ? fill_every_setting() : 0;
     const BwdImpl impl = bwd_impl();
+    if (impl == kBwdCol && bwd_col_eligible(a)) return launch_bwd_col<COMPOSITE>(a, st);
     if (impl == kBwdCta || impl == kBwdAuto) {
         static const int rd_on = env_flag("MOG_BWD_RD", 0);
         if (!COMPOSITE && rd_on && bwd_rd_eligible(a)) return launch_bwd_rd(a, st);
