@@ -336,11 +336,12 @@ static int launch_bwd_rd(const BwdArgs& a, cudaStream_t st) {
     return MOG_OK;
 }
 
-// MOG_BWD_IMPL selects the separable-theta backward (read once).  Default "auto": the CTA-per-image kernel where it is
-// eligible and measured faster (write direction onto outputs >= 192 columns wide: -25 ... -43 % on the 256-wide cells, a
-// tie at 128, slower below), the warp-per-image streaming kernel everywhere else.  "stream" / "cta" force one of the two
-// (cta falls back where ineligible); "group" (grouped gather form, register loads) and "tma" (grouped form, source and
-// gradient tiles staged by TMA) are the two experimental formulations kept for comparison (slower, see profiles/).
+// MOG_BWD_IMPL selects the separable-theta backward (read once).  Default "auto": the source-column kernel
+// (mog_stn_bwd_col.cuh) in the write direction (Wo >= Ws, Ho >= Hs, Ws <= 64: faster than every other form in all 12 sweep
+// cells, -25 ... -45 %), the warp-per-image streaming kernel in the read direction; where the source-column kernel is not
+// eligible the CTA-per-image kernel takes outputs >= 192 columns wide.  "stream" / "cta" / "col" force one form (falling
+// back where ineligible); "group" (grouped gather form, register loads) and "tma" (grouped form, source and gradient tiles
+// staged by TMA) are the two experimental formulations kept for comparison (slower, see profiles/).
 enum BwdImpl { kBwdStream = 0, kBwdGroup = 1, kBwdTma = 2, kBwdCta = 3, kBwdAuto = 4, kBwdCol = 5 };
 static BwdImpl bwd_impl() {
     static int v = -1;
@@ -363,7 +364,9 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     a.fill_every = a.coop_zero == 2 ? fill_every_setting() : 0;
     const BwdImpl impl = bwd_impl();
-    if (impl == kBwdCol && bwd_col_eligible(a)) return launch_bwd_col<COMPOSITE>(a, st);
+    // write direction (output at least as wide as the source): the source-column form wins in all 12 sweep cells
+    if ((impl == kBwdCol || (impl == kBwdAuto && a.g.Wo >= a.g.Ws && a.g.Ho >= a.g.Hs)) && bwd_col_eligible(a))
+        return launch_bwd_col<COMPOSITE>(a, st);
     if (impl == kBwdCta || impl == kBwdAuto) {
         static const int rd_on = env_flag("MOG_BWD_RD", 0);
         if (!COMPOSITE && rd_on && bwd_rd_eligible(a)) return launch_bwd_rd(a, st);

@@ -21,7 +21,13 @@
 
 namespace mog {
 
-constexpr int kColRB = 4;          // output rows per batch
+#ifndef MOG_COL_RB
+#define MOG_COL_RB 4
+#endif
+#ifndef MOG_COL_MINB
+#define MOG_COL_MINB 10   // 96 registers: 20 warps per SM (measured against 6 / 7 / 8 / 12, profiles/r02_kernel_experiments.md)
+#endif
+constexpr int kColRB = MOG_COL_RB;   // output rows per batch
 constexpr int kColMaxWs = 64;      // source columns: NCOL <= 2 per lane
 
 struct ColLayout {
@@ -38,7 +44,7 @@ __host__ __device__ inline ColLayout bwd_col_layout(const Geo& g) {
 }
 
 template <bool COMPOSITE, int NCOL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) stn_bwd_col_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MOG_COL_MINB) stn_bwd_col_kernel(const BwdArgs a) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const Geo& g = a.g;
     const ColLayout L = bwd_col_layout(g);
@@ -117,9 +123,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) stn_bwd_col_kernel(const Bw
                 }
                 const int nrows = ihi - ilo + 1;
                 const int4* rows = s_row + (ascending ? ilo : g.Ho - 1 - ihi);   // rows[ii] = stream row ii
-                const float* gfirst = gb + (long long)(ascending ? ilo : ihi) * g.Wo;
+                const int gfirst = (ascending ? ilo : ihi) * g.Wo;   // element offsets within the image's gradient (N < 2^31)
                 const int gstep = ascending ? g.Wo : -g.Wo;
-                const char* Uc = reinterpret_cast<const char*>(Ub) + x * 4;
+                const float* Ubx = Ub + x;
                 char* colp = reinterpret_cast<char*>(dUb) + x * 4;
                 bool tap_ok[NCOL + 1], col_ok[NCOL];
 #pragma unroll
@@ -155,8 +161,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) stn_bwd_col_kernel(const Bw
                         for (int r = 0; r < kColRB; ++r) {
 #pragma unroll
                             for (int k = 0; k <= NCOL; ++k) {
-                                Ia[r][k] = tap_ok[k] ? ldg_f32(Uc + cy[r].x + 4 * k) : 0.f;
-                                Ib[r][k] = tap_ok[k] ? ldg_f32(Uc + cy[r].x + ws4 + 4 * k) : 0.f;
+                                Ia[r][k] = tap_ok[k] ? __ldg(Ubx + ((cy[r].x >> 2) + k)) : 0.f;
+                                Ib[r][k] = tap_ok[k] ? __ldg(Ubx + ((cy[r].x >> 2) + g.Ws + k)) : 0.f;
                             }
                         }
 #pragma unroll
@@ -180,7 +186,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) stn_bwd_col_kernel(const Bw
 #pragma unroll
                         for (int c = 0; c < NCOL; ++c) { A[r][c] = 0.f; Bs[r][c] = 0.f; }
                     }
-                    const float* gbat = gfirst + (long long)ii0 * gstep;
+                    int grow[kColRB];   // offset of the batch's rows (rows past the end: the last valid one, masked below)
+#pragma unroll
+                    for (int r = 0; r < kColRB; ++r) grow[r] = gfirst + (ii0 + (r < nb ? r : nb - 1)) * gstep;
                     for (int q = 0; q < rmax; ++q) {
                         float gq[kColRB][NCOL];
                         int4 cj[NCOL];
@@ -192,7 +200,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) stn_bwd_col_kernel(const Bw
                             const int jj = valid[c] ? j : jlo;
                             cj[c] = s_col[jj];
 #pragma unroll
-                            for (int r = 0; r < kColRB; ++r) gq[r][c] = (valid[c] && r < nb) ? __ldg(gbat + r * gstep + jj) : 0.f;
+                            for (int r = 0; r < kColRB; ++r) {   // (always a valid address: the mask is applied to the value)
+                                const float gl = __ldg(gb + (grow[r] + jj));
+                                gq[r][c] = (valid[c] && r < nb) ? gl : 0.f;
+                            }
                         }
 #pragma unroll
                         for (int c = 0; c < NCOL; ++c) {

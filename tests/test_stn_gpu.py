@@ -3,6 +3,8 @@
 Contract: corner indices bit-exact; forward values bit-exact for finite inputs (same operation order,
 no FMA) with the SURVEY A.1 bound as the documented tolerance; gradients within GRAD_RTOL of the fp64
 oracle relative to the sum of |terms| (atomic / tree order makes them non-bit-exact)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -413,3 +415,46 @@ def test_backward_matches_autodiff_of_the_reference_source(cuda_device, name):
     _, dU, dth = run_fwd_bwd(cuda_device, z["U"][rows], z["theta"][rows], z["out_size"], z["gout"][rows])
     assert H.grad_excess(dU, g["dU"], z["absdU"][rows], rtol=2 * H.GRAD_RTOL) <= 1.0
     assert H.grad_excess(dth, g["dtheta"], z["absdtheta"][rows], rtol=2 * H.GRAD_RTOL) <= 1.0
+
+
+_IMPL_CASE = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from mog_asr_b200 import _lib, synth
+from oracle import stn_ref_numpy as R
+from tests import helpers as H
+dev = torch.device("cuda:0")
+L = _lib.load()
+worst = 0.0
+for (Hs, Ho, B, full) in ((28, 50, 33, False), (64, 256, 9, True), (64, 256, 9, False), (50, 28, 33, False), (64, 128, 17, True)):
+    rng = np.random.default_rng(Hs + Ho)
+    U = rng.random((B, Hs, Hs, 1), dtype=np.float32)
+    s, x, y = synth.sxy_full_cover(B, seed=3) if full else synth.sxy_prior_like(B, seed=3)
+    th = synth.theta_read(s, x, y) if Hs > Ho else synth.theta_write(s, x, y)
+    g = rng.normal(size=(B, Ho, Ho, 1)).astype(np.float32)
+    dU = torch.full((B, Hs, Hs, 1), float("nan"), device=dev); dth = torch.full((B, 6), float("nan"), device=dev)
+    Ud, thd, gd = (torch.tensor(a, device=dev) for a in (U, th, g))
+    rc = L.mog_stn_backward(Ud.data_ptr(), thd.data_ptr(), gd.data_ptr(), dU.data_ptr(), dth.data_ptr(), B, Hs, Hs, 1, Ho, Ho, 1, None)
+    torch.cuda.synchronize()
+    assert rc == 0
+    rU, rth = R.transformer_backward(U, th, (Ho, Ho), g)
+    aU, ath = R.backward_term_magnitudes(U, th, (Ho, Ho), g)
+    worst = max(worst, H.grad_excess(dU.cpu().numpy(), rU, aU), H.grad_excess(dth.cpu().numpy().reshape(-1, 2, 3), rth, ath))
+print("WORST", worst)
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("impl", ["stream", "cta", "col", "group", "tma"])
+def test_every_backward_formulation_meets_the_gradient_contract(cuda_device, impl):
+    """The library carries several formulations of the separable backward (MOG_BWD_IMPL, read once per process: hence the
+    subprocess): the streaming and source-column kernels are the shipped defaults, the CTA-per-image, grouped and TMA-ring
+    kernels are kept as measured alternatives.  Each must meet the same fp64-oracle tolerance in both directions."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MOG_BWD_IMPL=impl)
+    r = subprocess.run([sys.executable, "-c", _IMPL_CASE % root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().splitlines()[-1].split()[1])
+    assert worst <= 1.0, f"{impl}: excess over the gradient tolerance {worst}"
