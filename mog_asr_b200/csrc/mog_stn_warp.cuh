@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                             fill_zero_bulk(dUb, 0, ylo * g.Ws, lane, zero_smem);
                             fill_zero_bulk(dUb, yend * g.Ws, SC, lane, zero_smem);
                         }
-                        fill_zero(dUb, ylo * g.Ws, yend * g.Ws, lane);
+                        // (the band itself is zeroed just ahead of the stream, a few rows at a time: see band_off below)
                     } else if (!split) {
                         fill_zero_bulk(dUb, 0, SC, lane, zero_smem);
                     }
@@ -688,12 +688,24 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
                     int offcur = -1;  // byte offset of the source row held in acc0 (acc1: next row); -1 = none
                     const bool ascending = !(th.t[4] < 0.0f);
                     const int nrows = ihi - ilo + 1;
+                    // Large sources (bulk mode): the band rows are zeroed by ordinary stores just before the stream overwrites
+                    // them, the rows of one batch at a time (first strip pass; whole rows, one contiguous fill), so that the
+                    // zero and the value of a line meet in L2.  Zeroing the whole band up front cost a second DRAM write of
+                    // part of it (ncu, 256 <- 64: 5.37 GB of traffic for 4.79 GB of algorithmic bytes).  Zeroing only a strip's
+                    // own columns per pass was measured too: the per-row fills cost more instructions than the traffic saves.
+                    int band_off = ascending ? s_row[ilo].x : s_row[ihi].x;   // byte offset of the first band row not yet zeroed
                     const char* Ubc = opaque(reinterpret_cast<const char*>(Ub));
                     char* dUbc = reinterpret_cast<char*>(dUb) + (xlo + lane) * 4;
                     const int P = g.Wo + 1;  // pitch of the per-row ga/gb buffers; column Wo is a zero slot
 
                     for (int ii0 = 0; ii0 < nrows; ii0 += kBwdRB) {
                         const int nb = min(kBwdRB, nrows - ii0);
+                        if (bulk && first_pass) {   // zero the source rows this batch reaches (ordered before phase 2 by the __syncwarp below)
+                            const int ilast = ascending ? ilo + ii0 + nb - 1 : ihi - ii0 - nb + 1;
+                            const int upto = s_row[ilast].x + 2 * ws4;
+                            fill_zero(dUb, band_off >> 2, upto >> 2, lane);
+                            band_off = max(band_off, upto);
+                        }
                         // ---- phase 1 (output-column side): loads of kBwdRB rows in flight together ----
                         for (int jc = 0; jc < njc; ++jc) {
                             const int j = jlo + jc * 32 + lane;
