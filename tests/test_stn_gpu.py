@@ -426,7 +426,8 @@ from tests import helpers as H
 dev = torch.device("cuda:0")
 L = _lib.load()
 worst = 0.0
-for (Hs, Ho, B, full) in ((28, 50, 33, False), (64, 256, 9, True), (64, 256, 9, False), (50, 28, 33, False), (64, 128, 17, True)):
+for (Hs, Ho, B, full) in ((28, 50, 33, False), (64, 256, 9, True), (64, 256, 9, False), (50, 28, 33, False), (64, 128, 17, True),
+                          (256, 64, 13, False), (256, 64, 13, True)):
     rng = np.random.default_rng(Hs + Ho)
     U = rng.random((B, Hs, Hs, 1), dtype=np.float32)
     s, x, y = synth.sxy_full_cover(B, seed=3) if full else synth.sxy_prior_like(B, seed=3)
@@ -445,7 +446,7 @@ print("WORST", worst)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("impl", ["stream", "cta", "col", "group", "tma"])
+@pytest.mark.parametrize("impl", ["stream", "cta", "col", "group", "tma", "rd", "fill_split"])
 def test_every_backward_formulation_meets_the_gradient_contract(cuda_device, impl):
     """The library carries several formulations of the separable backward (MOG_BWD_IMPL, read once per process: hence the
     subprocess): the streaming and source-column kernels are the shipped defaults, the CTA-per-image, grouped and TMA-ring
@@ -453,7 +454,13 @@ def test_every_backward_formulation_meets_the_gradient_contract(cuda_device, imp
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MOG_BWD_IMPL=impl)
+    env = dict(os.environ)
+    if impl == "rd":                  # warp-specialised read backward (2 fill warps + 2 compute warps per CTA)
+        env.update(MOG_BWD_IMPL="auto", MOG_BWD_RD="1")
+    elif impl == "fill_split":        # every third CTA only feeds the bulk-copy engine
+        env.update(MOG_BWD_IMPL="stream", MOG_FILL_EVERY="3")
+    else:
+        env["MOG_BWD_IMPL"] = impl
     r = subprocess.run([sys.executable, "-c", _IMPL_CASE % root], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(r.stdout.strip().splitlines()[-1].split()[1])
