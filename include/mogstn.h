@@ -108,6 +108,27 @@ MOG_API int mog_stn_write_composite_backward(const float* U, const float* theta,
                                      float* dtheta, float* dz, int64_t B, int Hw, int Ww, int Hc, int Wc,
                                      void* stream);
 
+/* The two sampler calls of an AIR step with theta built in the kernel from the model's (s, x, y) -- SURVEY 8(f)2: "pass 3
+ * floats, return ds, dx, dy directly".  shift [B][2] = (x, y) (tanh output, :435-436), scale [B] = s (sigmoid output,
+ * :458-459); read: theta = [[s,0,x],[0,s,y]] (air_number_bbox_location.py:511-531), write: theta = [[1/s,0,-x/s],[0,1/s,-y/s]]
+ * (:563-584), evaluated with the same fp32 expressions as mog_air_thetas_forward, so outputs equal those of the theta-taking
+ * entry points bit for bit.  C = 1.  The backward writes d_shift [B][2] and d_scale [B] (fully overwritten); g_shift_in /
+ * g_scale_in (nullable) are added to them -- the gradient that reached the same (s, x, y) through the step's other sampler
+ * call -- so no accumulation kernel is needed.  dU / dz nullable as in the theta-taking forms. */
+MOG_API int mog_stn_read_sxy_forward(const float* U, const float* shift, const float* scale, float* out, int64_t B, int Hs,
+                             int Ws, int Ho, int Wo, void* stream);
+MOG_API int mog_stn_read_sxy_backward(const float* U, const float* shift, const float* scale, const float* gout,
+                              const float* g_shift_in, const float* g_scale_in, float* dU, float* d_shift,
+                              float* d_scale, int64_t B, int Hs, int Ws, int Ho, int Wo, void* stream);
+MOG_API int mog_stn_write_composite_sxy_forward(const float* U, const float* shift, const float* scale, const float* z_pres,
+                                        const float* stop_sum, float threshold, const float* canvas_in,
+                                        float* canvas_out, int64_t B, int Hw, int Ww, int Hc, int Wc, void* stream);
+MOG_API int mog_stn_write_composite_sxy_backward(const float* U, const float* shift, const float* scale, const float* z_pres,
+                                         const float* stop_sum, float threshold, const float* gcanvas,
+                                         const float* g_shift_in, const float* g_scale_in, float* dU, float* d_shift,
+                                         float* d_scale, float* dz, int64_t B, int Hw, int Ww, int Hc, int Wc,
+                                         void* stream);
+
 /* The write call site of the AIR loop on HOST buffers (air_number_bbox_location.py:592-600 and :718-727): T windows per
  * image are written onto ONE canvas per image, canvas[b] = sum_t z[t][b] * sample(W[t][b]; theta[t][b]) (accumulated in
  * step order, exactly as T calls of mog_stn_write_composite_forward on a zero canvas), and gcanvas_h = d loss / d canvas

@@ -42,6 +42,10 @@ SIGNATURES = {
     "mog_stn_batch_host_workspace_bytes": [_i64, _int, _int, _int, _int, _int, _int, _int],
     "mog_stn_write_composite_forward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
     "mog_stn_write_composite_backward": [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
+    "mog_stn_read_sxy_forward": [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
+    "mog_stn_read_sxy_backward": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
+    "mog_stn_write_composite_sxy_forward": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
+    "mog_stn_write_composite_sxy_backward": [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _vp],
     "mog_stn_write_composite_host": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _i64, _vp, ctypes.c_size_t,
                                      ctypes.POINTER(ctypes.c_void_p), _int],
     "mog_stn_write_composite_host_workspace_bytes": [_i64, _int, _int, _int, _int, _int, _int],

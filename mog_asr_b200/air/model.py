@@ -97,6 +97,22 @@ class CudaOps:
         from ..composite import write_composite
         return write_composite(canvas, window, theta, z_pres, stop_sum, threshold)
 
+    def read_sxy(self, images4, inf_shift, inf_scale, out_size):
+        """glimpse read with theta built in the kernel (``mog_asr_b200/sxy.py``); returns (window, shift, scale) -- the returned
+        shift / scale go to ``write_composite_sxy`` so that their two gradients meet inside the read call's backward kernel"""
+        if self.fused_pointwise:
+            from ..sxy import read_glimpse_sxy
+            return read_glimpse_sxy(images4, inf_shift, inf_scale, out_size)
+        theta_r, _ = self.thetas(inf_shift, inf_scale)
+        return self.transformer(images4, theta_r, out_size), inf_shift, inf_scale
+
+    def write_composite_sxy(self, canvas, window, shift, scale, z_pres, stop_sum, threshold):
+        if self.fused_pointwise:
+            from ..sxy import write_composite_sxy
+            return write_composite_sxy(canvas, window, shift, scale, z_pres, stop_sum, threshold)
+        _, theta_w = self.thetas(shift, scale)
+        return self.write_composite(canvas, window, theta_w, z_pres, stop_sum, threshold)
+
     def recon_loss(self, images, canvas):
         from ..recon import reconstruction_loss
         return reconstruction_loss(canvas, images)[0]
@@ -564,8 +580,8 @@ class AIRModel(nn.Module):
             gen_out, gen_state = self.gen_cell(prev, gen_state, pointwise=lstm_pw)                          # :465-470
             g_sh_mean, g_sh_lv = self.gen_shift(gen_out)                                                    # :472-481
 
-            theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)                                        # :511-531,:563-584
-            window = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws, ws)                      # :534-542
+            window, w_shift, w_scale = self.ops.read_sxy(images4, inf_shift, inf_scale, (ws, ws))           # :511-542 (theta_r in the kernel)
+            window = window.reshape(B, ws, ws)
             recon, v_mean, v_lv, v_latent = self._vae(window.reshape(B, ws * ws), noise("vae", step, (B, L)))  # :544-553
 
             if cfg.fix_steps is not None:                                                                   # :604-608
@@ -584,7 +600,7 @@ class AIRModel(nn.Module):
                 stop_sum = stop_sum + (1.0 - z_pres)                                                          # :712
                 active = stop_sum < thr
             act_list.append(active)
-            canvas = self.ops.write_composite(canvas, recon.reshape(B, ws, ws), theta_w, z_pres, stop_sum, thr)  # :592-600,:722-727
+            canvas = self.ops.write_composite_sxy(canvas, recon.reshape(B, ws, ws), w_shift, w_scale, z_pres, stop_sum, thr)  # :563-600,:722-727
 
             if cfg.stacked_kl:
                 # the KL terms are elementwise functions of per-step tensors: keep those, evaluate after the loop
@@ -627,7 +643,7 @@ class AIRModel(nn.Module):
         # ---- the recurrence proper -------------------------------------------------------------------------
         inf_state = (z(B, H), z(B, H))
         prev_latent, prev_ss = z(B, L), z(B, 3)
-        per = {k: [] for k in ("out", "prev", "latent", "theta_w", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "v_mean", "v_lv",
+        per = {k: [] for k in ("out", "prev", "latent", "w_sxy", "sc_mean", "sc_lv", "sh_mean", "sh_lv", "v_mean", "v_lv",
                                "shift", "scale")}
         for step in range(T):
             prev = torch.cat([prev_latent, prev_ss], -1)
@@ -635,10 +651,10 @@ class AIRModel(nn.Module):
             sh_mean, sh_lv, shift_latent, inf_shift = self.inf_shift.sample(self.ops, out, noise("shift", step, (B, 2)), "tanh")
             sc_mean, sc_lv, scale_latent, inf_scale = self.inf_scale.sample(self.ops, out, noise("scale", step, (B, 1)), "sigmoid",
                                                                             skip=shift_latent)
-            theta_r, theta_w = self.ops.thetas(inf_shift, inf_scale)
-            x = self.ops.transformer(images4, theta_r, (ws, ws)).reshape(B, ws * ws)   # C = 1: a view, no select
+            x, w_shift, w_scale = self.ops.read_sxy(images4, inf_shift, inf_scale, (ws, ws))   # theta_r built in the kernel
+            x = x.reshape(B, ws * ws)                                                  # C = 1: a view, no select
             v_mean, v_lv, v_latent = self._encode(x, noise("vae", step, (B, L)))
-            for k, v in (("out", out), ("prev", prev), ("latent", v_latent), ("theta_w", theta_w), ("sc_mean", sc_mean),
+            for k, v in (("out", out), ("prev", prev), ("latent", v_latent), ("w_sxy", (w_shift, w_scale)), ("sc_mean", sc_mean),
                          ("sc_lv", sc_lv), ("sh_mean", sh_mean), ("sh_lv", sh_lv), ("v_mean", v_mean), ("v_lv", v_lv),
                          ("shift", inf_shift), ("scale", inf_scale)):
                 per[k].append(v)
@@ -677,7 +693,7 @@ class AIRModel(nn.Module):
         for step in range(T):
             y_pre, z_pres, stop_sum, active_prev, active = self.ops.zpres(post_lo_t[step], noise("concrete", step, (B,)), stop_sum,
                                                                           temp, thr)
-            canvas = self.ops.write_composite(canvas, recon[step], per["theta_w"][step], z_pres, stop_sum, thr)
+            canvas = self.ops.write_composite_sxy(canvas, recon[step], *per["w_sxy"][step], z_pres, stop_sum, thr)
             y_pre_l.append(y_pre); act_prev_l.append(active_prev); act_l.append(active)
 
         if side is not None:

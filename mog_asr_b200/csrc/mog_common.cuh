@@ -98,6 +98,18 @@ struct Theta {
 #pragma unroll
         for (int k = 0; k < 6; ++k) t[k] = __ldg(p + k);
     }
+    // theta built in the kernel from the model's (s, x, y) (air_number_bbox_location.py:511-531, :563-584), same fp32
+    // expressions as mog_air_thetas_forward: mode 1 (read) [[s,0,x],[0,s,y]], mode 2 (write) [[1/s,0,-x/s],[0,1/s,-y/s]]
+    __device__ __forceinline__ void load_sxy(const float* __restrict__ shift, const float* __restrict__ scale, long long b, int mode) {
+        const float s = __ldg(scale + b), x = __ldg(shift + 2 * b), y = __ldg(shift + 2 * b + 1);
+        t[1] = 0.0f; t[3] = 0.0f;
+        if (mode == 1) {
+            t[0] = s; t[2] = x; t[4] = s; t[5] = y;
+        } else {
+            const float inv = 1.0f / s;
+            t[0] = inv; t[2] = -x / s; t[4] = inv; t[5] = -y / s;
+        }
+    }
     // axis-aligned transform: x_s depends on j only, y_s on i only.  With t01 == 0 the middle product
     // is +-0 and (t00*x_t + +-0) + t02 equals t00*x_t + t02 after the "+1" of transformer.py:75, so the
     // per-column / per-row tables are bit-identical to the per-pixel evaluation.

@@ -363,6 +363,10 @@ static int launch_bwd(BwdArgs a, cudaStream_t st) {
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     a.fill_every = a.coop_zero == 2 ? fill_every_setting() : 0;
+    if (a.sxy_mode) {   // theta built in the kernel: the two shipped formulations carry that path
+        if (a.g.Wo >= a.g.Ws && a.g.Ho >= a.g.Hs && bwd_col_eligible(a)) return launch_bwd_col<COMPOSITE>(a, st);
+        return launch_bwd_stream<COMPOSITE>(a, st);
+    }
     const BwdImpl impl = bwd_impl();
     // write direction (output at least as wide as the source): the source-column form wins in all 12 sweep cells
     if ((impl == kBwdCol || (impl == kBwdAuto && a.g.Wo >= a.g.Ws && a.g.Ho >= a.g.Hs)) && bwd_col_eligible(a))
@@ -466,6 +470,63 @@ extern "C" int mog_stn_write_composite_backward(const float* U, const float* the
     BwdArgs a{};
     a.U = U; a.theta = theta; a.gout = gcanvas; a.dU = dU; a.dtheta = dtheta; a.z_pres = z_pres;
     a.stop_sum = stop_sum; a.dz = dz; a.threshold = threshold; a.Bsrc = B; a.u_div = 1;
+    a.g = make_geo(Hw, Ww, 1, Hc, Wc);
+    return launch_bwd<true>(a, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The two sampler calls of an AIR step with theta built in the kernel from the model's (s, x, y)
+// (air_number_bbox_location.py:511-542 read, :563-600 + :718-727 write): shift [B][2] = (x, y), scale [B] = s.
+// The backward returns d_shift / d_scale directly; g_shift_in / g_scale_in (nullable) are added to them, so the gradient that
+// reached the same (s, x, y) through the step's other call needs no accumulation kernel.
+// ---------------------------------------------------------------------------------------------------
+extern "C" int mog_stn_read_sxy_forward(const float* U, const float* shift, const float* scale, float* out, int64_t B, int Hs,
+                                        int Ws, int Ho, int Wo, void* stream) {
+    if (int rc = check_dims(B, Hs, Ws, 1, Ho, Wo, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && shift && scale && out), MOG_ERR_NULL, "mog_stn_read_sxy_forward: NULL pointer");
+    FwdArgs a{};
+    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 1; a.out = out; a.B = B; a.u_div = 1;
+    a.g = make_geo(Hs, Ws, 1, Ho, Wo);
+    return launch_fwd<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_read_sxy_backward(const float* U, const float* shift, const float* scale, const float* gout,
+                                         const float* g_shift_in, const float* g_scale_in, float* dU, float* d_shift,
+                                         float* d_scale, int64_t B, int Hs, int Ws, int Ho, int Wo, void* stream) {
+    if (int rc = check_dims(B, Hs, Ws, 1, Ho, Wo, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && shift && scale && gout && d_shift && d_scale), MOG_ERR_NULL, "mog_stn_read_sxy_backward: NULL pointer");
+    BwdArgs a{};
+    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 1; a.g_shift_in = g_shift_in; a.g_scale_in = g_scale_in;
+    a.d_shift = d_shift; a.d_scale = d_scale; a.gout = gout; a.dU = dU; a.Bsrc = B; a.u_div = 1;
+    a.g = make_geo(Hs, Ws, 1, Ho, Wo);
+    return launch_bwd<false>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_write_composite_sxy_forward(const float* U, const float* shift, const float* scale, const float* z_pres,
+                                                   const float* stop_sum, float threshold, const float* canvas_in,
+                                                   float* canvas_out, int64_t B, int Hw, int Ww, int Hc, int Wc, void* stream) {
+    if (int rc = check_dims(B, Hw, Ww, 1, Hc, Wc, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && shift && scale && z_pres && canvas_in && canvas_out), MOG_ERR_NULL,
+                "mog_stn_write_composite_sxy_forward: NULL pointer");
+    FwdArgs a{};
+    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 2; a.out = canvas_out; a.z_pres = z_pres; a.stop_sum = stop_sum;
+    a.canvas_in = canvas_in; a.threshold = threshold; a.B = B; a.u_div = 1;
+    a.g = make_geo(Hw, Ww, 1, Hc, Wc);
+    return launch_fwd<true>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mog_stn_write_composite_sxy_backward(const float* U, const float* shift, const float* scale, const float* z_pres,
+                                                    const float* stop_sum, float threshold, const float* gcanvas,
+                                                    const float* g_shift_in, const float* g_scale_in, float* dU, float* d_shift,
+                                                    float* d_scale, float* dz, int64_t B, int Hw, int Ww, int Hc, int Wc,
+                                                    void* stream) {
+    if (int rc = check_dims(B, Hw, Ww, 1, Hc, Wc, 1)) return rc;
+    MOG_REQUIRE(B == 0 || (U && shift && scale && z_pres && gcanvas && d_shift && d_scale), MOG_ERR_NULL,
+                "mog_stn_write_composite_sxy_backward: NULL pointer");
+    BwdArgs a{};
+    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 2; a.g_shift_in = g_shift_in; a.g_scale_in = g_scale_in;
+    a.d_shift = d_shift; a.d_scale = d_scale; a.gout = gcanvas; a.dU = dU; a.z_pres = z_pres; a.stop_sum = stop_sum; a.dz = dz;
+    a.threshold = threshold; a.Bsrc = B; a.u_div = 1;
     a.g = make_geo(Hw, Ww, 1, Hc, Wc);
     return launch_bwd<true>(a, (cudaStream_t)stream);
 }

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MOG_COL_MINB) stn_bwd_col_k
         float* __restrict__ dUb = a.dU ? a.dU + b * (long long)SC : nullptr;
         const float* __restrict__ gb = a.gout + b * (long long)g.N;
         Theta th;
-        th.load(a.theta + 6 * b);
+        MOG_LOAD_THETA(th, a, b);
         float z = 1.0f;
         bool active = true;
         if (COMPOSITE) {
@@ -269,10 +269,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MOG_COL_MINB) stn_bwd_col_k
 #pragma unroll
         for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
         if (lane == 0) {
-            if (a.dtheta) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) a.dtheta[6 * b + k] = p[k];
-            }
+            MOG_STORE_DTHETA(a, b, p);
             if (COMPOSITE && a.dz) a.dz[b] = p[6];
         }
     }

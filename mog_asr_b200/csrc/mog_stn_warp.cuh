@@ -44,6 +44,10 @@ constexpr int kWarpThreads = kWarpsPerCta * 32;
 struct FwdArgs {
     const float* U;
     const float* theta;
+    // sxy_mode != 0: theta is built in the kernel from shift [B][2] and scale [B] (1 = read, 2 = write); theta is unused
+    const float* shift;
+    const float* scale;
+    int sxy_mode;
     float* out;
     // composite only
     const float* z_pres;
@@ -60,6 +64,16 @@ struct FwdArgs {
 struct BwdArgs {
     const float* U;
     const float* theta;
+    // sxy_mode != 0: theta from (shift, scale) as in FwdArgs; the gradient is returned as d_shift [B][2], d_scale [B]
+    // (dtheta unused), plus the optional add-ins g_shift_in / g_scale_in (gradients that reached the same shift / scale
+    // through the other sampler call of the step)
+    const float* shift;
+    const float* scale;
+    const float* g_shift_in;
+    const float* g_scale_in;
+    float* d_shift;
+    float* d_scale;
+    int sxy_mode;
     const float* gout;
     float* dU;
     float* dtheta;
@@ -75,6 +89,45 @@ struct BwdArgs {
     int fill_every; // > 0 (with coop_zero == 2): every fill_every-th CTA only feeds the copy engine, the others never wait for it
     Geo g;
 };
+
+// (scalar arguments only: taking the address of the kernel-parameter struct would force a local copy of it)
+__device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ theta, const float* __restrict__ shift,
+                                           const float* __restrict__ scale, int sxy_mode, long long b) {
+    if (sxy_mode) th.load_sxy(shift, scale, b, sxy_mode);
+    else th.load(theta + 6 * b);
+}
+#define MOG_LOAD_THETA(th, a, b) load_theta(th, (a).theta, (a).shift, (a).scale, (a).sxy_mode, b)
+
+// one lane writes the image's transform gradient: dtheta [6], or -- theta built from (s, x, y) -- d_shift, d_scale by the
+// chain rule of Theta::load_sxy (the arithmetic of mog_air_thetas_backward)
+__device__ __forceinline__ void store_dtheta(float* __restrict__ dtheta, const float* __restrict__ shift,
+                                             const float* __restrict__ scale, const float* __restrict__ g_shift_in,
+                                             const float* __restrict__ g_scale_in, float* __restrict__ d_shift,
+                                             float* __restrict__ d_scale, int sxy_mode, long long b, const float (&p)[7]) {
+    if (sxy_mode == 0) {
+        if (dtheta) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) dtheta[6 * b + k] = p[k];
+        }
+        return;
+    }
+    if (!d_shift || !d_scale) return;
+    float ds, dx, dy;
+    if (sxy_mode == 1) {
+        ds = p[0] + p[4]; dx = p[2]; dy = p[5];
+    } else {
+        const float s = __ldg(scale + b), x = __ldg(shift + 2 * b), y = __ldg(shift + 2 * b + 1);
+        const float inv = 1.0f / s, inv2 = inv * inv;
+        ds = (x * p[2] + y * p[5]) * inv2 - (p[0] + p[4]) * inv2;
+        dx = -p[2] * inv; dy = -p[5] * inv;
+    }
+    if (g_scale_in) ds += __ldg(g_scale_in + b);
+    if (g_shift_in) { dx += __ldg(g_shift_in + 2 * b); dy += __ldg(g_shift_in + 2 * b + 1); }
+    d_scale[b] = ds;
+    d_shift[2 * b] = dx; d_shift[2 * b + 1] = dy;
+}
+#define MOG_STORE_DTHETA(a, b, p) \
+    store_dtheta((a).dtheta, (a).shift, (a).scale, (a).g_shift_in, (a).g_scale_in, (a).d_shift, (a).d_scale, (a).sxy_mode, b, p)
 
 // row-table entry: {y0*Ws, y1*Ws, ay, by}; column entry: {x0, x1, ax, bx}
 __device__ __forceinline__ int4 row_entry(const Theta& th, const Geo& g, int i) {
@@ -259,7 +312,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kerne
         if (blockIdx.x % R == R - 1 && blockIdx.x / R < nfill) {
             for (long long b = (long long)(blockIdx.x / R) * kWarpsPerCta + warp; b < a.B; b += nfill * kWarpsPerCta) {
                 Theta th;
-                th.load(a.theta + 6 * b);
+                MOG_LOAD_THETA(th, a, b);
                 if (!(th.separable() && C == 1)) continue;   // the sampling side writes such an image whole
                 int ilo = g.Ho, ihi = -1;
                 for (int i = lane; i < g.Ho; i += 32) {
@@ -282,7 +335,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kerne
     const long long nwarps_c = ncta * kWarpsPerCta;
     for (long long b = cta * kWarpsPerCta + warp; b < a.B; b += nwarps_c) {
         Theta th;
-        th.load(a.theta + 6 * b);
+        MOG_LOAD_THETA(th, a, b);
         const bool sep = th.separable();
         float z = 1.0f;
         bool active = true;
@@ -530,7 +583,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
             const int ws4f = g.Ws * 4;
             for (long long bs = (long long)(blockIdx.x / R) * kWarpsPerCta + warp; bs < a.Bsrc; bs += nfill * kWarpsPerCta) {
                 Theta th;
-                th.load(a.theta + 6 * bs);
+                MOG_LOAD_THETA(th, a, bs);
                 if (!(th.separable() && C == 1)) continue;   // the general path zero-fills such an image itself
                 int ilo = g.Ho, ihi = -1, jlo = g.Wo, jhi = -1;
                 for (int i = lane; i < g.Ho; i += 32) {
@@ -581,7 +634,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
         for (int t = 0; t < a.u_div; ++t) {
             const long long b = bs * a.u_div + t;
             Theta th;
-            th.load(a.theta + 6 * b);
+            MOG_LOAD_THETA(th, a, b);
             const bool sep = th.separable() && C == 1;
             float z = 1.0f;
             bool active = true;
@@ -821,10 +874,7 @@ __global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kerne
 #pragma unroll
             for (int k = 0; k < 7; ++k) p[k] = warp_sum(p[k]);
             if (lane == 0) {
-                if (a.dtheta) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) a.dtheta[6 * b + k] = p[k];
-                }
+                MOG_STORE_DTHETA(a, b, p);
                 if (COMPOSITE && a.dz) a.dz[b] = p[6];
             }
         }

@@ -23,6 +23,15 @@ class OracleOps:
         win = stn_ref_torch.transformer(window[..., None], theta, (cs, cs))[..., 0]
         return canvas + torch.where((stop_sum < threshold)[:, None, None], z_pres[:, None, None] * win, torch.zeros_like(win))
 
+    def read_sxy(self, images4, inf_shift, inf_scale, out_size):
+        """the read call site as the model states it (theta from (s, x, y), :511-542); returns (window, shift, scale)"""
+        theta_r, _ = self.thetas(inf_shift, inf_scale)
+        return self.transformer(images4, theta_r, out_size), inf_shift, inf_scale
+
+    def write_composite_sxy(self, canvas, window, shift, scale, z_pres, stop_sum, threshold):
+        _, theta_w = self.thetas(shift, scale)                                                 # :563-584
+        return self.write_composite(canvas, window, theta_w, z_pres, stop_sum, threshold)
+
     def recon_loss(self, images, canvas):
         r = torch.clamp(canvas, 0.0, 1.0)                                   # air_number_bbox_location.py:947-948
         return -(images * torch.log(r + 1e-10) + (1.0 - images) * torch.log(1.0 - r + 1e-10)).sum(1)   # :954-959

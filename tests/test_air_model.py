@@ -323,14 +323,21 @@ def test_graph_step_with_parallel_branches_equals_single_stream_graph(cuda_devic
         tr.capture(B)
         assert all(torch.equal(a, b) for a, b in zip(before, tr.params)) and tr.t == 0 and float(tr.t_dev) == 0.0
         torch.cuda.manual_seed(777)                      # identical noise streams for both captures
-        for _ in range(3):
+        out = tr.step_graph(images)
+        torch.cuda.synchronize()
+        first_grad = tr.flat_grad.detach().clone()       # the gradient of the first replay: same weights in both captures
+        for _ in range(2):
             out = tr.step_graph(images)
         torch.cuda.synchronize()
         assert torch.isfinite(out["loss"]).all()
-        finals.append([p.detach().clone() for p in tr.params])
-    for a, b in zip(*finals):
-        # Adam moves every weight by ~lr per step; identical gradients up to atomic order leave the updates within a few % of lr
-        assert float((a - b).abs().max()) <= 3e-5, float((a - b).abs().max())
+        finals.append(([p.detach().clone() for p in tr.params], first_grad))
+    (pa, ga), (pb, gb) = finals
+    # identical up to the order of the head kernels' atomics
+    assert float((ga - gb).abs().max()) <= 1e-5 * float(gb.abs().max()), (float((ga - gb).abs().max()), float(gb.abs().max()))
+    for a, b in zip(pa, pb):
+        # Adam moves every weight by ~lr = 1e-4 per step whatever the gradient's size, so an entry whose gradient is rounding
+        # noise may differ by a good part of one step after three; anything systematic would show up as several steps
+        assert float((a - b).abs().max()) <= 1e-4, float((a - b).abs().max())
 
 
 @pytest.mark.gpu

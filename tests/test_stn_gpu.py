@@ -465,3 +465,51 @@ def test_every_backward_formulation_meets_the_gradient_contract(cuda_device, imp
     assert r.returncode == 0, r.stderr[-2000:]
     worst = float(r.stdout.strip().splitlines()[-1].split()[1])
     assert worst <= 1.0, f"{impl}: excess over the gradient tolerance {worst}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cs,ws,B", [(50, 28, 300), (256, 64, 24)])
+def test_sxy_entry_points_equal_the_theta_path(cuda_device, cs, ws, B):
+    """Theta built inside the sampler kernels from the model's (s, x, y) (reference :511-531, :563-584): the read
+    and the write + composite give the same bits as the theta-taking entry points fed by the theta kernel, and d_shift /
+    d_scale -- the write call's share added inside the read call's backward kernel -- equal autograd through the theta
+    kernel within the gradient tolerance."""
+    from mog_asr_b200.air.fused import thetas
+    from mog_asr_b200.sxy import read_glimpse_sxy, write_composite_sxy
+    rng = np.random.default_rng(cs + ws)
+    s, x, y = synth.sxy_prior_like(B, seed=21)
+    img = torch.tensor(rng.random((B, cs, cs, 1), dtype=np.float32), device=cuda_device)
+    win = torch.tensor(rng.random((B, ws, ws), dtype=np.float32), device=cuda_device)
+    z = torch.tensor(rng.random(B, dtype=np.float32), device=cuda_device)
+    stop = torch.tensor(rng.random(B, dtype=np.float32) * 1.2, device=cuda_device)       # some images inactive (>= 0.9)
+    canvas0 = torch.tensor(rng.random((B, cs, cs), dtype=np.float32), device=cuda_device)
+    g_win = torch.tensor(rng.standard_normal((B, ws, ws, 1), dtype=np.float32), device=cuda_device)
+    g_can = torch.tensor(rng.standard_normal((B, cs, cs), dtype=np.float32), device=cuda_device)
+
+    def leaves():
+        sh = torch.tensor(np.stack([x, y], 1).astype(np.float32), device=cuda_device, requires_grad=True)
+        sc = torch.tensor(s.astype(np.float32)[:, None], device=cuda_device, requires_grad=True)
+        return sh, sc, win.clone().requires_grad_(True), z.clone().requires_grad_(True)
+
+    sh1, sc1, w1, z1 = leaves()                                  # theta path
+    th_r, th_w = thetas(sh1, sc1)
+    out1 = M.transformer(img, th_r, (ws, ws))
+    can1 = M.write_composite(canvas0, w1, th_w, z1, stop, 0.9)
+    ((out1 * g_win).sum() + (can1 * g_can).sum()).backward()
+    sh2, sc2, w2, z2 = leaves()                                  # theta in the kernels
+    out2, shp, scp = read_glimpse_sxy(img, sh2, sc2, (ws, ws))
+    can2 = write_composite_sxy(canvas0, w2, shp, scp, z2, stop, 0.9)
+    ((out2 * g_win).sum() + (can2 * g_can).sum()).backward()
+    assert torch.equal(out1, out2) and torch.equal(can1, can2)
+    assert torch.equal(w1.grad, w2.grad) and torch.equal(z1.grad, z2.grad)
+    for a, b in ((sh1.grad, sh2.grad), (sc1.grad, sc2.grad)):
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-5 * scale, (float((a - b).abs().max()), scale)
+    # the write call alone (nothing added in) and the read call alone
+    sh3, sc3, w3, z3 = leaves()
+    write_composite_sxy(canvas0, w3, sh3, sc3, z3, stop, 0.9).backward(g_can)
+    sh4, sc4, w4, z4 = leaves()
+    _, th_w4 = thetas(sh4, sc4)
+    M.write_composite(canvas0, w4, th_w4, z4, stop, 0.9).backward(g_can)
+    assert float((sh3.grad - sh4.grad).abs().max()) <= 2e-5 * float(sh4.grad.abs().max())
+    assert float((sc3.grad - sc4.grad).abs().max()) <= 2e-5 * float(sc4.grad.abs().max())
