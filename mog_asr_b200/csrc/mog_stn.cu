@@ -146,38 +146,52 @@ static int fill_every_setting() {
 }
 
 template <bool COMPOSITE>
-static int launch_fwd(FwdArgs a, cudaStream_t st) {
+static int launch_fwd(FwdArgs a, cudaStream_t st, const SxyArgs* sxy = nullptr) {
+    const SxyArgs sx = sxy ? *sxy : SxyArgs{};
     if (a.B == 0) return MOG_OK;
     a.bulk_zero = (!COMPOSITE && MOG_BULK_ZERO && (long long)a.g.N * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS) ? 1 : 0;
     a.fill_every = a.bulk_zero ? fill_every_setting() : 0;
     const size_t smem = (size_t)kWarpsPerCta * (a.g.Ho + a.g.Wo) * sizeof(int4) + (a.bulk_zero ? kZeroBytes : 0);
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d too large for the per-warp tables", a.g.Ho, a.g.Wo);
-    if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE>, smem)) return rc;
+    constexpr int kSxy = COMPOSITE ? 2 : 1;   // theta from (s, x, y): the plain call is the read, the composite the write
     const long long ctas = (a.B + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_fwd_warp_kernel<COMPOSITE><<<grid_for(ctas, MOG_FWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
+    if (sxy) {
+        if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE, kSxy>, smem)) return rc;
+        stn_fwd_warp_kernel<COMPOSITE, kSxy><<<grid_for(ctas, MOG_FWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a, sx);
+    } else {
+        if (int rc = set_smem(stn_fwd_warp_kernel<COMPOSITE, 0>, smem)) return rc;
+        stn_fwd_warp_kernel<COMPOSITE, 0><<<grid_for(ctas, MOG_FWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a, sx);
+    }
     MOG_CUDA_LAUNCH_CHECK("stn_fwd_warp_kernel");
     return MOG_OK;
 }
 
 template <bool COMPOSITE, int NXC>
-static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st) {
+static int launch_bwd_nxc(const BwdArgs& a, cudaStream_t st, const SxyArgs* sxy = nullptr) {
+    const SxyArgs sx = sxy ? *sxy : SxyArgs{};
     const size_t smem = (size_t)kWarpsPerCta * bwd_warp_smem_words(a.g) * sizeof(int) + (a.coop_zero == 2 ? kZeroBytes : 0);
     MOG_REQUIRE(smem <= (size_t)kMaxSmemBytes, MOG_ERR_UNSUPPORTED, "Ho=%d Wo=%d Ws=%d too large for the per-warp tables",
                 a.g.Ho, a.g.Wo, a.g.Ws);
-    if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC>, smem)) return rc;
+    constexpr int kSxy = COMPOSITE ? 2 : 1;
     const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_bwd_warp_kernel<COMPOSITE, NXC><<<grid_for(ctas, MOG_BWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a);
+    if (sxy) {
+        if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC, kSxy>, smem)) return rc;
+        stn_bwd_warp_kernel<COMPOSITE, NXC, kSxy><<<grid_for(ctas, MOG_BWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a, sx);
+    } else {
+        if (int rc = set_smem(stn_bwd_warp_kernel<COMPOSITE, NXC, 0>, smem)) return rc;
+        stn_bwd_warp_kernel<COMPOSITE, NXC, 0><<<grid_for(ctas, MOG_BWD_GRID_PER_SM), kWarpThreads, smem, st>>>(a, sx);
+    }
     MOG_CUDA_LAUNCH_CHECK("stn_bwd_warp_kernel");
     return MOG_OK;
 }
 
 template <bool COMPOSITE>
-static int launch_bwd_stream(const BwdArgs& a, cudaStream_t st) {
+static int launch_bwd_stream(const BwdArgs& a, cudaStream_t st, const SxyArgs* sxy = nullptr) {
     // NXC = source-column chunks (of 32) kept in registers per streaming pass; wider footprints are strip-mined
     const int nxc = (a.g.Ws + 31) / 32;
-    if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st);
-    if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st);
-    return launch_bwd_nxc<COMPOSITE, 4>(a, st);
+    if (nxc <= 1) return launch_bwd_nxc<COMPOSITE, 1>(a, st, sxy);
+    if (nxc <= 2) return launch_bwd_nxc<COMPOSITE, 2>(a, st, sxy);
+    return launch_bwd_nxc<COMPOSITE, 4>(a, st, sxy);
 }
 
 template <bool COMPOSITE, int NJC>
@@ -302,21 +316,26 @@ static bool bwd_col_eligible(const BwdArgs& a) {
 }
 
 template <bool COMPOSITE, int NCOL>
-static int launch_bwd_col_n(const BwdArgs& a, cudaStream_t st) {
+static int launch_bwd_col_n(const BwdArgs& a, cudaStream_t st, const SxyArgs* sxy) {
+    const SxyArgs sx = sxy ? *sxy : SxyArgs{};
     const size_t smem = (size_t)bwd_col_layout(a.g).total * kWarpsPerCta;
-    if (int rc = set_smem(stn_bwd_col_kernel<COMPOSITE, NCOL>, smem)) return rc;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stn_bwd_col_kernel<COMPOSITE, NCOL>, kWarpsPerCta * 32, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
-    stn_bwd_col_kernel<COMPOSITE, NCOL><<<grid_for(ctas, per_sm), kWarpsPerCta * 32, smem, st>>>(a);
+    constexpr int kSxy = COMPOSITE ? 2 : 1;
+    auto launch = [&](auto kernel) -> int {
+        if (int rc = set_smem(kernel, smem)) return rc;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerCta * 32, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const long long ctas = (a.Bsrc + kWarpsPerCta - 1) / kWarpsPerCta;
+        kernel<<<grid_for(ctas, per_sm), kWarpsPerCta * 32, smem, st>>>(a, sx);
+        return MOG_OK;
+    };
+    if (int rc = sxy ? launch(stn_bwd_col_kernel<COMPOSITE, NCOL, kSxy>) : launch(stn_bwd_col_kernel<COMPOSITE, NCOL, 0>)) return rc;
     MOG_CUDA_LAUNCH_CHECK("stn_bwd_col_kernel");
     return MOG_OK;
 }
 
 template <bool COMPOSITE>
-static int launch_bwd_col(const BwdArgs& a, cudaStream_t st) {
-    return a.g.Ws <= 32 ? launch_bwd_col_n<COMPOSITE, 1>(a, st) : launch_bwd_col_n<COMPOSITE, 2>(a, st);
+static int launch_bwd_col(const BwdArgs& a, cudaStream_t st, const SxyArgs* sxy = nullptr) {
+    return a.g.Ws <= 32 ? launch_bwd_col_n<COMPOSITE, 1>(a, st, sxy) : launch_bwd_col_n<COMPOSITE, 2>(a, st, sxy);
 }
 
 // Read direction with dU (mog_stn_bwd_rd.cuh): large source, glimpse-sized output, fill and arithmetic in different warps.
@@ -358,14 +377,14 @@ static BwdImpl bwd_impl() {
 }
 
 template <bool COMPOSITE>
-static int launch_bwd(BwdArgs a, cudaStream_t st) {
+static int launch_bwd(BwdArgs a, cudaStream_t st, const SxyArgs* sxy = nullptr) {
     if (a.Bsrc == 0) return MOG_OK;
     a.coop_zero = (long long)a.g.S * a.g.C >= MOG_COOP_ZERO_MIN_FLOATS ? 1 : 0;
     if (a.coop_zero && MOG_BULK_ZERO && a.dU && a.u_div == 1 && a.g.C == 1) a.coop_zero = 2;
     a.fill_every = a.coop_zero == 2 ? fill_every_setting() : 0;
-    if (a.sxy_mode) {   // theta built in the kernel: the two shipped formulations carry that path
-        if (a.g.Wo >= a.g.Ws && a.g.Ho >= a.g.Hs && bwd_col_eligible(a)) return launch_bwd_col<COMPOSITE>(a, st);
-        return launch_bwd_stream<COMPOSITE>(a, st);
+    if (sxy) {   // theta built in the kernel: the two shipped formulations carry that path
+        if (a.g.Wo >= a.g.Ws && a.g.Ho >= a.g.Hs && bwd_col_eligible(a)) return launch_bwd_col<COMPOSITE>(a, st, sxy);
+        return launch_bwd_stream<COMPOSITE>(a, st, sxy);
     }
     const BwdImpl impl = bwd_impl();
     // write direction (output at least as wide as the source): the source-column form wins in all 12 sweep cells
@@ -485,9 +504,10 @@ extern "C" int mog_stn_read_sxy_forward(const float* U, const float* shift, cons
     if (int rc = check_dims(B, Hs, Ws, 1, Ho, Wo, 1)) return rc;
     MOG_REQUIRE(B == 0 || (U && shift && scale && out), MOG_ERR_NULL, "mog_stn_read_sxy_forward: NULL pointer");
     FwdArgs a{};
-    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 1; a.out = out; a.B = B; a.u_div = 1;
+    a.U = U; a.out = out; a.B = B; a.u_div = 1;
     a.g = make_geo(Hs, Ws, 1, Ho, Wo);
-    return launch_fwd<false>(a, (cudaStream_t)stream);
+    const SxyArgs sx{shift, scale, nullptr, nullptr, nullptr, nullptr};
+    return launch_fwd<false>(a, (cudaStream_t)stream, &sx);
 }
 
 extern "C" int mog_stn_read_sxy_backward(const float* U, const float* shift, const float* scale, const float* gout,
@@ -496,10 +516,10 @@ extern "C" int mog_stn_read_sxy_backward(const float* U, const float* shift, con
     if (int rc = check_dims(B, Hs, Ws, 1, Ho, Wo, 1)) return rc;
     MOG_REQUIRE(B == 0 || (U && shift && scale && gout && d_shift && d_scale), MOG_ERR_NULL, "mog_stn_read_sxy_backward: NULL pointer");
     BwdArgs a{};
-    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 1; a.g_shift_in = g_shift_in; a.g_scale_in = g_scale_in;
-    a.d_shift = d_shift; a.d_scale = d_scale; a.gout = gout; a.dU = dU; a.Bsrc = B; a.u_div = 1;
+    a.U = U; a.gout = gout; a.dU = dU; a.Bsrc = B; a.u_div = 1;
     a.g = make_geo(Hs, Ws, 1, Ho, Wo);
-    return launch_bwd<false>(a, (cudaStream_t)stream);
+    const SxyArgs sx{shift, scale, g_shift_in, g_scale_in, d_shift, d_scale};
+    return launch_bwd<false>(a, (cudaStream_t)stream, &sx);
 }
 
 extern "C" int mog_stn_write_composite_sxy_forward(const float* U, const float* shift, const float* scale, const float* z_pres,
@@ -509,10 +529,11 @@ extern "C" int mog_stn_write_composite_sxy_forward(const float* U, const float* 
     MOG_REQUIRE(B == 0 || (U && shift && scale && z_pres && canvas_in && canvas_out), MOG_ERR_NULL,
                 "mog_stn_write_composite_sxy_forward: NULL pointer");
     FwdArgs a{};
-    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 2; a.out = canvas_out; a.z_pres = z_pres; a.stop_sum = stop_sum;
+    a.U = U; a.out = canvas_out; a.z_pres = z_pres; a.stop_sum = stop_sum;
     a.canvas_in = canvas_in; a.threshold = threshold; a.B = B; a.u_div = 1;
     a.g = make_geo(Hw, Ww, 1, Hc, Wc);
-    return launch_fwd<true>(a, (cudaStream_t)stream);
+    const SxyArgs sx{shift, scale, nullptr, nullptr, nullptr, nullptr};
+    return launch_fwd<true>(a, (cudaStream_t)stream, &sx);
 }
 
 extern "C" int mog_stn_write_composite_sxy_backward(const float* U, const float* shift, const float* scale, const float* z_pres,
@@ -524,11 +545,11 @@ extern "C" int mog_stn_write_composite_sxy_backward(const float* U, const float*
     MOG_REQUIRE(B == 0 || (U && shift && scale && z_pres && gcanvas && d_shift && d_scale), MOG_ERR_NULL,
                 "mog_stn_write_composite_sxy_backward: NULL pointer");
     BwdArgs a{};
-    a.U = U; a.shift = shift; a.scale = scale; a.sxy_mode = 2; a.g_shift_in = g_shift_in; a.g_scale_in = g_scale_in;
-    a.d_shift = d_shift; a.d_scale = d_scale; a.gout = gcanvas; a.dU = dU; a.z_pres = z_pres; a.stop_sum = stop_sum; a.dz = dz;
+    a.U = U; a.gout = gcanvas; a.dU = dU; a.z_pres = z_pres; a.stop_sum = stop_sum; a.dz = dz;
     a.threshold = threshold; a.Bsrc = B; a.u_div = 1;
     a.g = make_geo(Hw, Ww, 1, Hc, Wc);
-    return launch_bwd<true>(a, (cudaStream_t)stream);
+    const SxyArgs sx{shift, scale, g_shift_in, g_scale_in, d_shift, d_scale};
+    return launch_bwd<true>(a, (cudaStream_t)stream, &sx);
 }
 
 // ---------------------------------------------------------------------------------------------------

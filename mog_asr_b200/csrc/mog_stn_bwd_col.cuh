@@ -43,8 +43,8 @@ __host__ __device__ inline ColLayout bwd_col_layout(const Geo& g) {
     return l;
 }
 
-template <bool COMPOSITE, int NCOL>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MOG_COL_MINB) stn_bwd_col_kernel(const BwdArgs a) {
+template <bool COMPOSITE, int NCOL, int SXY>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MOG_COL_MINB) stn_bwd_col_kernel(const BwdArgs a, const SxyArgs sx) {
     extern __shared__ __align__(128) unsigned char s_raw[];
     const Geo& g = a.g;
     const ColLayout L = bwd_col_layout(g);

@@ -44,10 +44,6 @@ constexpr int kWarpThreads = kWarpsPerCta * 32;
 struct FwdArgs {
     const float* U;
     const float* theta;
-    // sxy_mode != 0: theta is built in the kernel from shift [B][2] and scale [B] (1 = read, 2 = write); theta is unused
-    const float* shift;
-    const float* scale;
-    int sxy_mode;
     float* out;
     // composite only
     const float* z_pres;
@@ -61,19 +57,23 @@ struct FwdArgs {
     Geo g;
 };
 
-struct BwdArgs {
-    const float* U;
-    const float* theta;
-    // sxy_mode != 0: theta from (shift, scale) as in FwdArgs; the gradient is returned as d_shift [B][2], d_scale [B]
-    // (dtheta unused), plus the optional add-ins g_shift_in / g_scale_in (gradients that reached the same shift / scale
-    // through the other sampler call of the step)
+// Theta built in the kernel from the model's (s, x, y) (template parameter SXY of the kernels: 1 = read, 2 = write; theta in
+// FwdArgs / BwdArgs is then unused): shift [B][2], scale [B]; the backward returns d_shift [B][2], d_scale [B] plus the
+// optional add-ins g_shift_in / g_scale_in (gradients that reached the same shift / scale through the step's other sampler
+// call).  A kernel parameter of its own, so that FwdArgs / BwdArgs -- and with them the code generated for the theta-taking
+// kernels -- are what they were before this path existed.
+struct SxyArgs {
     const float* shift;
     const float* scale;
     const float* g_shift_in;
     const float* g_scale_in;
     float* d_shift;
     float* d_scale;
-    int sxy_mode;
+};
+
+struct BwdArgs {
+    const float* U;
+    const float* theta;
     const float* gout;
     float* dU;
     float* dtheta;
@@ -90,13 +90,13 @@ struct BwdArgs {
     Geo g;
 };
 
-// (scalar arguments only: taking the address of the kernel-parameter struct would force a local copy of it)
-__device__ __forceinline__ void load_theta(Theta& th, const float* __restrict__ theta, const float* __restrict__ shift,
-                                           const float* __restrict__ scale, int sxy_mode, long long b) {
-    if (sxy_mode) th.load_sxy(shift, scale, b, sxy_mode);
-    else th.load(theta + 6 * b);
-}
-#define MOG_LOAD_THETA(th, a, b) load_theta(th, (a).theta, (a).shift, (a).scale, (a).sxy_mode, b)
+// SXY (template parameter of the kernels): 0 = theta given, 1 / 2 = theta built from (s, x, y) for the read / write call;
+// compile time, so that the theta-taking kernels are exactly what they were before this path existed
+#define MOG_LOAD_THETA(th, a, b)                                              \
+    do {                                                                      \
+        if constexpr (SXY != 0) (th).load_sxy(sx.shift, sx.scale, b, SXY);    \
+        else (th).load((a).theta + 6 * (b));                                  \
+    } while (0)
 
 // one lane writes the image's transform gradient: dtheta [6], or -- theta built from (s, x, y) -- d_shift, d_scale by the
 // chain rule of Theta::load_sxy (the arithmetic of mog_air_thetas_backward)
@@ -127,7 +127,7 @@ __device__ __forceinline__ void store_dtheta(float* __restrict__ dtheta, const f
     d_shift[2 * b] = dx; d_shift[2 * b + 1] = dy;
 }
 #define MOG_STORE_DTHETA(a, b, p) \
-    store_dtheta((a).dtheta, (a).shift, (a).scale, (a).g_shift_in, (a).g_scale_in, (a).d_shift, (a).d_scale, (a).sxy_mode, b, p)
+    store_dtheta((a).dtheta, sx.shift, sx.scale, sx.g_shift_in, sx.g_scale_in, sx.d_shift, sx.d_scale, SXY, b, p)
 
 // row-table entry: {y0*Ws, y1*Ws, ay, by}; column entry: {x0, x1, ax, bx}
 __device__ __forceinline__ int4 row_entry(const Theta& th, const Geo& g, int i) {
@@ -282,8 +282,8 @@ __device__ __noinline__ void fwd_general_image(const float* __restrict__ Ub, flo
 // ---------------------------------------------------------------------------------------------------
 // forward (also the fused write+composite forward)
 // ---------------------------------------------------------------------------------------------------
-template <bool COMPOSITE>
-__global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kernel(const FwdArgs a) {
+template <bool COMPOSITE, int SXY>
+__global__ void __launch_bounds__(kWarpThreads, MOG_FWD_MINB) stn_fwd_warp_kernel(const FwdArgs a, const SxyArgs sx) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
@@ -541,8 +541,8 @@ __device__ __noinline__ void bwd_general_image(const float* __restrict__ Ub, flo
     }
 }
 
-template <bool COMPOSITE, int NXC>
-__global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kernel(const BwdArgs a) {
+template <bool COMPOSITE, int NXC, int SXY>
+__global__ void __launch_bounds__(kWarpThreads, MOG_BWD_MINB) stn_bwd_warp_kernel(const BwdArgs a, const SxyArgs sx) {
     extern __shared__ int4 s_dyn[];
     const Geo& g = a.g;
     const int C = g.C;
