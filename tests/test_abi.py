@@ -79,6 +79,29 @@ def test_host_wrappers_refuse_cpu_tensors():
         m.transformer(torch.zeros(1, 4, 4, 1), torch.zeros(1, 6), (2, 2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.write_composite(torch.zeros(1, 4, 4), torch.zeros(1, 2, 2), torch.zeros(1, 6), torch.zeros(1))
+    from mog_asr_b200.host_api import HostCompositeWriter, HostSampler
+    from mog_asr_b200.sxy import read_glimpse_sxy, write_composite_sxy
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        read_glimpse_sxy(torch.zeros(1, 4, 4, 1), torch.zeros(1, 2), torch.ones(1), (2, 2))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        write_composite_sxy(torch.zeros(1, 4, 4), torch.zeros(1, 2, 2), torch.zeros(1, 2), torch.ones(1), torch.zeros(1))
+    for ctor in (lambda: HostSampler("cpu", (4, 4), (2, 2)), lambda: HostCompositeWriter("cpu", (2, 2), (4, 4), steps=2)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ctor()
+
+
+def test_zero_batch_is_a_no_op_for_the_newer_entry_points(lib):
+    """argument checks and the B = 0 early-outs run on the host: no GPU needed"""
+    assert lib.mog_stn_read_sxy_forward(None, None, None, None, 0, 50, 50, 28, 28, None) == 0
+    assert lib.mog_stn_read_sxy_backward(None, None, None, None, None, None, None, None, None, 0, 50, 50, 28, 28, None) == 0
+    assert lib.mog_stn_write_composite_sxy_forward(None, None, None, None, None, 0.9, None, None, 0, 28, 28, 50, 50, None) == 0
+    assert lib.mog_stn_write_composite_sxy_backward(None, None, None, None, None, 0.9, None, None, None, None, None, None, None,
+                                                    0, 28, 28, 50, 50, None) == 0
+    assert lib.mog_stn_write_composite_host(None, None, None, None, None, None, None, None, 0, 8, 28, 28, 50, 50, 64, None, 0, None, 3) == 0
+    assert lib.mog_stn_write_composite_host_workspace_bytes(64, 8, 28, 28, 50, 50, 3) > 0
+    assert lib.mog_stn_write_composite_host_workspace_bytes(0, 8, 28, 28, 50, 50, 3) == 0
+    assert lib.mog_stn_read_sxy_forward(None, None, None, None, 4, 50, 50, 28, 28, None) < 0        # NULL pointers with B > 0
+    assert lib.mog_stn_read_sxy_forward(None, None, None, None, 4, 0, 50, 28, 28, None) < 0         # bad dimension
 
 
 def test_product_package_never_imports_the_oracle():
